@@ -1,0 +1,577 @@
+// gf_oracle.cpp -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE)
+//
+// A plain C++17 restatement of the math on Gaugefields.jl's quenched SU(3)
+// Wilson update path, used ONLY as the checker for the CUDA library
+// (tests/, __graft_entry__.smoke(), bench.py's cpu_baseline / --impl reference
+// legs).  Nothing under gaugefields.jl_b200/ may include, link or call this.
+//
+// Parity status: PINNED against the reference's own golden values
+//   * legacy "Reproducible" hot start (StableRNG(123)) 4^4 SU(3) plaquette
+//     0.008449494077606137              (test/init.jl:276-283)
+//   * 4^4 SU(3) Wilson flow, 100 x eps=0.01, plaquette 0.8786515255315753
+//                                        (test/gradientflow_test.jl:129-139)
+//   * cold start invariants, MD reversibility < 2e-12, force additivity
+//                                        (test/md_driver.jl:371-395, 417-482)
+//   * SU(2)-embedded one-instanton plaquette 0.9796864531099871
+//                                        (test/init.jl:351-371)
+// UNPINNED (LatticeMatrices.jl is not vendored): the Philox key schedule of
+// the LM site streams; the Philox-keyed hot start / Gaussian fill below follow
+// the reference's *stream structure* (test/MPIJACCtest/random_fields_site_rng.jl:22-42)
+// with a key schedule defined in DESIGN.md.
+//
+// Every function cites the reference file:line (relative to /root/reference)
+// whose behaviour it restates.  Storage is the reference's host layout:
+//   links   ComplexF64[3,3,NX,NY,NZ,NT] column-major per direction (src/API.jl:516-529)
+//   momenta Float64[8,1,NX,NY,NZ,NT]                        (TA_gaugefields_4D_MPILattice.jl:34-35)
+// with the 4 directions stored back to back.
+
+#include <complex>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+
+typedef std::complex<double> cd;
+
+namespace {
+
+struct M3 {
+    cd a[3][3];
+};
+
+inline M3 zero3() { M3 r; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) r.a[i][j] = 0.0; return r; }
+inline M3 ident3() { M3 r = zero3(); for (int i = 0; i < 3; i++) r.a[i][i] = 1.0; return r; }
+inline M3 mul(const M3& x, const M3& y) {
+    M3 r;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            cd s = 0.0;
+            for (int k = 0; k < 3; k++) s += x.a[i][k] * y.a[k][j];
+            r.a[i][j] = s;
+        }
+    return r;
+}
+inline M3 dag(const M3& x) { M3 r; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) r.a[i][j] = std::conj(x.a[j][i]); return r; }
+inline M3 add(const M3& x, const M3& y) { M3 r; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) r.a[i][j] = x.a[i][j] + y.a[i][j]; return r; }
+inline M3 sub(const M3& x, const M3& y) { M3 r; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) r.a[i][j] = x.a[i][j] - y.a[i][j]; return r; }
+inline M3 scale(cd s, const M3& x) { M3 r; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) r.a[i][j] = s * x.a[i][j]; return r; }
+inline cd trace(const M3& x) { return x.a[0][0] + x.a[1][1] + x.a[2][2]; }
+inline double norm1(const M3& x) { double m = 0; for (int j = 0; j < 3; j++) { double s = 0; for (int i = 0; i < 3; i++) s += std::abs(x.a[i][j]); m = std::max(m, s); } return m; }
+
+struct Lat {
+    int n[4];
+    long V;
+    explicit Lat(const int* d) { for (int i = 0; i < 4; i++) n[i] = d[i]; V = (long)n[0] * n[1] * n[2] * n[3]; }
+    inline long idx(const int* x) const { return x[0] + (long)n[0] * (x[1] + (long)n[1] * (x[2] + (long)n[2] * x[3])); }
+    inline void coord(long s, int* x) const { for (int i = 0; i < 4; i++) { x[i] = (int)(s % n[i]); s /= n[i]; } }
+};
+
+// link accessor in the reference host layout (element (i,j) at i + 3*j, src/API.jl:516-529)
+inline M3 getU(const double* U, const Lat& L, int mu, long s) {
+    const double* p = U + ((long)mu * L.V + s) * 18;
+    M3 r;
+    for (int j = 0; j < 3; j++) for (int i = 0; i < 3; i++) r.a[i][j] = cd(p[2 * (i + 3 * j)], p[2 * (i + 3 * j) + 1]);
+    return r;
+}
+inline void setU(double* U, const Lat& L, int mu, long s, const M3& m) {
+    double* p = U + ((long)mu * L.V + s) * 18;
+    for (int j = 0; j < 3; j++) for (int i = 0; i < 3; i++) { p[2 * (i + 3 * j)] = m.a[i][j].real(); p[2 * (i + 3 * j) + 1] = m.a[i][j].imag(); }
+}
+
+// Ordered product of links along a path starting at site x.
+// A step (mu,+1) multiplies by U_mu(y) and moves y -> y+mu; a step (mu,-1) moves
+// y -> y-mu first and multiplies by U_mu(y)^dagger.  Periodic wrap.
+// Restates evaluate_gaugelinks! (src/AbstractGaugefields.jl:1797-1862) with the
+// shift semantics of src/4D/nowing/gaugefields_4D_nowing.jl:380-412.
+struct Step { int mu; int sgn; };
+inline M3 path_product(const double* U, const Lat& L, const int* x0, const Step* st, int nst) {
+    int y[4] = {x0[0], x0[1], x0[2], x0[3]};
+    M3 r = ident3();
+    for (int k = 0; k < nst; k++) {
+        int mu = st[k].mu;
+        if (st[k].sgn > 0) {
+            r = mul(r, getU(U, L, mu, L.idx(y)));
+            y[mu] = (y[mu] + 1) % L.n[mu];
+        } else {
+            y[mu] = (y[mu] + L.n[mu] - 1) % L.n[mu];
+            r = mul(r, dag(getU(U, L, mu, L.idx(y))));
+        }
+    }
+    return r;
+}
+
+const double SR3 = std::sqrt(3.0);
+
+// Traceless anti-Hermitian projection to 8 Gell-Mann coefficients,
+// TA(M) = sum_a c_a * i*lambda_a/2.  Restates
+// src/4D/TA_gaugefields_4D_serial.jl:181-269.
+inline void ta_coeffs(const M3& m, double* c) {
+    M3 y;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) y.a[i][j] = 0.5 * (m.a[i][j] - std::conj(m.a[j][i]));
+    cd tr = trace(y) / 3.0;
+    for (int i = 0; i < 3; i++) y.a[i][i] -= tr;
+    c[0] = y.a[0][1].imag() + y.a[1][0].imag();
+    c[1] = y.a[0][1].real() - y.a[1][0].real();
+    c[2] = y.a[0][0].imag() - y.a[1][1].imag();
+    c[3] = y.a[0][2].imag() + y.a[2][0].imag();
+    c[4] = y.a[0][2].real() - y.a[2][0].real();
+    c[5] = y.a[1][2].imag() + y.a[2][1].imag();
+    c[6] = y.a[1][2].real() - y.a[2][1].real();
+    c[7] = (y.a[0][0].imag() + y.a[1][1].imag() - 2.0 * y.a[2][2].imag()) / SR3;
+}
+
+// matrix-valued projection Q = (M-M^dag)/2 - tr/3 (src/4D/nowing/gaugefields_4D_nowing.jl:1253-1345)
+inline M3 ta_matrix(const M3& m) {
+    M3 y;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) y.a[i][j] = 0.5 * (m.a[i][j] - std::conj(m.a[j][i]));
+    cd tr = trace(y) / 3.0;
+    for (int i = 0; i < 3; i++) y.a[i][i] -= tr;
+    return y;
+}
+
+// Hermitian matrix H = sum_a c_a lambda_a / 2 (src/4D/TA_gaugefields_4D_serial.jl:779-847)
+inline M3 hermitian_from_coeffs(const double* u, double t) {
+    double c[8];
+    for (int a = 0; a < 8; a++) c[a] = t * u[a] * 0.5;
+    M3 h;
+    h.a[0][0] = c[2] + c[7] / SR3;
+    h.a[0][1] = cd(c[0], -c[1]);
+    h.a[0][2] = cd(c[3], -c[4]);
+    h.a[1][0] = cd(c[0], c[1]);
+    h.a[1][1] = -c[2] + c[7] / SR3;
+    h.a[1][2] = cd(c[5], -c[6]);
+    h.a[2][0] = cd(c[3], c[4]);
+    h.a[2][1] = cd(c[5], c[6]);
+    h.a[2][2] = -2.0 * c[7] / SR3;
+    return h;
+}
+
+// exp of a general 3x3 complex matrix by scaling-and-squaring Taylor series
+// (accurate to ~1e-16; independent of both the legacy eigen route and the
+// Cayley-Hamilton route used on the GPU).
+inline M3 exp_taylor(const M3& x) {
+    double nrm = norm1(x);
+    int s = 0;
+    while (nrm > 0.125) { nrm *= 0.5; s++; }
+    M3 y = scale(std::ldexp(1.0, -s), x);
+    M3 r = ident3();
+    M3 term = ident3();
+    for (int n = 1; n <= 18; n++) {
+        term = scale(1.0 / n, mul(term, y));
+        r = add(r, term);
+    }
+    for (int k = 0; k < s; k++) r = mul(r, r);
+    return r;
+}
+
+// exp(i H), H Hermitian traceless, via the closed-form eigenvalues (trigonometric
+// cubic solution) and spectral projectors.  Follows the eigen-decomposition route
+// of exptU! (src/4D/TA_gaugefields_4D_serial.jl:850-1074) without its tinyvalue /
+// Taylor-4 artefacts: near-degenerate spectra fall back to exp_taylor.
+inline M3 exp_iH_eigen(const M3& h, bool* used_fallback) {
+    const double PI23 = 2.0 * M_PI / 3.0;
+    M3 h2 = mul(h, h);
+    double c1 = 0.5 * trace(h2).real();                 // = -p of the depressed cubic  e^3 - c1 e - c0 = 0
+    cd det = h.a[0][0] * (h.a[1][1] * h.a[2][2] - h.a[1][2] * h.a[2][1]) - h.a[0][1] * (h.a[1][0] * h.a[2][2] - h.a[1][2] * h.a[2][0]) +
+             h.a[0][2] * (h.a[1][0] * h.a[2][1] - h.a[1][1] * h.a[2][0]);
+    double c0 = det.real();
+    *used_fallback = false;
+    if (c1 < 1e-6) { *used_fallback = true; return exp_taylor(scale(cd(0, 1), h)); }
+    double r = 2.0 * std::sqrt(c1 / 3.0);
+    double arg = 3.0 * c0 / (c1 * r);
+    arg = std::min(1.0, std::max(-1.0, arg));
+    double th = std::acos(arg) / 3.0;
+    double e[3] = {r * std::cos(th), r * std::cos(th + PI23), 0.0};
+    e[2] = -e[0] - e[1];
+    double gap = std::min({std::abs(e[0] - e[1]), std::abs(e[1] - e[2]), std::abs(e[0] - e[2])});
+    if (gap < 1e-3 * r) { *used_fallback = true; return exp_taylor(scale(cd(0, 1), h)); }
+    // spectral projectors P_k = prod_{l != k} (H - e_l)/(e_k - e_l)
+    M3 out = zero3();
+    for (int k = 0; k < 3; k++) {
+        int l1 = (k + 1) % 3, l2 = (k + 2) % 3;
+        M3 a = h, b = h;
+        for (int i = 0; i < 3; i++) { a.a[i][i] -= e[l1]; b.a[i][i] -= e[l2]; }
+        M3 p = scale(1.0 / ((e[k] - e[l1]) * (e[k] - e[l2])), mul(a, b));
+        out = add(out, scale(cd(std::cos(e[k]), std::sin(e[k])), p));
+    }
+    return out;
+}
+
+// exp(t * sum_a u_a i lambda_a/2): exptU! for TA fields (src/4D/TA_gaugefields_4D_serial.jl:760-848)
+inline M3 exp_ta(const double* u, double t, int route) {
+    M3 h = hermitian_from_coeffs(u, t);
+    if (route == 1) { bool fb; return exp_iH_eigen(h, &fb); }
+    return exp_taylor(scale(cd(0, 1), h));
+}
+
+// ---------------------------------------------------------------------------------------------
+// RNG
+// ---------------------------------------------------------------------------------------------
+
+// StableRNGs.jl LehmerRNG (un-vendored dependency, StableRNGs 1.x, Project.toml:48): 128-bit
+// multiplicative congruential generator, state = (seed<<1)|1, output = high 64 bits;
+// rand(Float64) = reinterpret(0x3ff0...|low52(u64)) - 1.  Pinned by the golden plaquette
+// 0.008449494077606137 (test/init.jl:281), which only this variant reproduces.
+struct Lehmer {
+    unsigned __int128 state;
+    explicit Lehmer(uint64_t seed) { state = (((unsigned __int128)seed) << 1) | 1; }
+    inline uint64_t u64() {
+        const unsigned __int128 mult = (((unsigned __int128)0x45a31efc5a35d971ULL) << 64) | 0x261fd0407a968addULL;
+        state *= mult;
+        return (uint64_t)(state >> 64);
+    }
+    inline double f64() {
+        uint64_t b = 0x3ff0000000000000ULL | (u64() & 0x000fffffffffffffULL);
+        double d; std::memcpy(&d, &b, 8);
+        return d - 1.0;
+    }
+};
+
+// Philox4x32-10 (Salmon et al. 2011).  Used for the decomposition-independent per-global-site
+// streams (structure: test/MPIJACCtest/random_fields_site_rng.jl:22-42; key schedule: DESIGN.md).
+inline void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// stream key for (seed, sweep, direction, tag): first two words of Philox((seed,sweep),(tag,direction))
+inline void stream_key(uint64_t seed, uint64_t sweep, uint32_t direction, uint32_t tag, uint32_t key[2]) {
+    uint32_t ctr[4] = {(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)sweep, (uint32_t)(sweep >> 32)};
+    uint32_t k[2] = {tag, direction};
+    uint32_t o[4];
+    philox4x32_10(ctr, k, o);
+    key[0] = o[0]; key[1] = o[1];
+}
+// two uniforms in [0,1) from draw `n` of the stream of global site `gsite`
+inline void site_uniform_pair(const uint32_t key[2], uint64_t gsite, uint32_t n, double* u0, double* u1) {
+    uint32_t ctr[4] = {(uint32_t)gsite, (uint32_t)(gsite >> 32), n, 0u};
+    uint32_t o[4];
+    philox4x32_10(ctr, key, o);
+    uint64_t a = ((uint64_t)o[1] << 32) | o[0], b = ((uint64_t)o[3] << 32) | o[2];
+    *u0 = (double)(a >> 11) * 0x1.0p-53;
+    *u1 = (double)(b >> 11) * 0x1.0p-53;
+}
+
+const uint32_t TAG_HOT = 0x00484f54u;    // src/AbstractGaugefields.jl:121-123
+const uint32_t TAG_GAUSS = 0x47415553u;
+
+// SU(3) reunitarisation: row-1 normalise, row-2 Gram-Schmidt, row 3 = conj(row1 x row2)
+// (src/4D/nowing/gaugefields_4D_nowing.jl:2387-2458 and :195-238)
+inline M3 reunitarize(const M3& m) {
+    M3 u = m;
+    cd w1 = 0.0, w2 = 0.0;
+    for (int c = 0; c < 3; c++) { w1 += u.a[1][c] * std::conj(u.a[0][c]); w2 += u.a[0][c] * std::conj(u.a[0][c]); }
+    w1 = -w1 / w2;
+    cd x[3];
+    for (int c = 0; c < 3; c++) x[c] = u.a[1][c] + w1 * u.a[0][c];
+    cd w3 = 0.0;
+    for (int c = 0; c < 3; c++) w3 += x[c] * std::conj(x[c]);
+    cd s3 = 1.0 / std::sqrt(w3), s2 = 1.0 / std::sqrt(w2);
+    for (int c = 0; c < 3; c++) { u.a[0][c] = u.a[0][c] * s2; u.a[1][c] = x[c] * s3; }
+    u.a[2][0] = std::conj(u.a[0][1] * u.a[1][2] - u.a[0][2] * u.a[1][1]);
+    u.a[2][1] = std::conj(u.a[0][2] * u.a[1][0] - u.a[0][0] * u.a[1][2]);
+    u.a[2][2] = std::conj(u.a[0][0] * u.a[1][1] - u.a[0][1] * u.a[1][0]);
+    return u;
+}
+
+// sum over the two plaquette-type closed loops through U_mu(x) in the (mu,nu) plane:
+//   U_mu(x) * [upper staple]^dag-type product, i.e. the loops (mu,nu,-mu,-nu) and (mu,-nu,-mu,nu).
+// Their sum over nu equals U_mu(x) * V_mu(x)^dagger with V_mu the 6-staple sum of
+// src/autostaples/wilsonloops.jl:468-484 / construct_double_staple! (src/AbstractGaugefields.jl:2856-2871).
+inline M3 U_times_Vdag(const double* U, const Lat& L, const int* x, int mu) {
+    M3 acc = zero3();
+    for (int nu = 0; nu < 4; nu++) {
+        if (nu == mu) continue;
+        Step up[4] = {{mu, 1}, {nu, 1}, {mu, -1}, {nu, -1}};
+        Step dn[4] = {{mu, 1}, {nu, -1}, {mu, -1}, {nu, 1}};
+        acc = add(acc, path_product(U, L, x, up, 4));
+        acc = add(acc, path_product(U, L, x, dn, 4));
+    }
+    return acc;
+}
+
+// the staple sum V_mu(x) itself (needed by stout: C_mu = rho * V_mu)
+inline M3 staple_sum(const double* U, const Lat& L, const int* x, int mu) {
+    M3 acc = zero3();
+    for (int nu = 0; nu < 4; nu++) {
+        if (nu == mu) continue;
+        Step up[3] = {{nu, 1}, {mu, 1}, {nu, -1}};
+        Step dn[3] = {{nu, -1}, {mu, 1}, {nu, 1}};
+        acc = add(acc, path_product(U, L, x, up, 3));
+        acc = add(acc, path_product(U, L, x, dn, 3));
+    }
+    return acc;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ----------------------------------------------------------------------------- initial fields
+
+void orc_set_cold(double* U, const int* dims) {
+    Lat L(dims);
+    M3 one = ident3();
+    for (int mu = 0; mu < 4; mu++) for (long s = 0; s < L.V; s++) setU(U, L, mu, s, one);
+}
+
+// legacy "Reproducible" hot start: every direction re-seeds StableRNG(123)
+// (src/4D/nowing/gaugefields_4D_nowing.jl:240-279; Appendix B of SURVEY.md)
+void orc_hot_start_stable123(double* U, const int* dims) {
+    Lat L(dims);
+    for (int mu = 0; mu < 4; mu++) {
+        Lehmer rng(123);
+        for (long s = 0; s < L.V; s++) {  // it,iz,iy,ix loops with ix fastest == linear site order
+            M3 m;
+            for (int j = 0; j < 3; j++) for (int i = 0; i < 3; i++) { double re = rng.f64() - 0.5; double im = rng.f64() - 0.5; m.a[i][j] = cd(re, im); }
+            setU(U, L, mu, s, reunitarize(m));
+        }
+    }
+}
+
+// Philox-keyed hot start: stream (seed, 0, mu+1, tag HOT) per global site
+// (structure of src/4D/mpi_jacc/gaugefields_4D_MPILattice.jl:430-472)
+void orc_hot_start_philox(double* U, const int* dims, uint64_t seed) {
+    Lat L(dims);
+    for (int mu = 0; mu < 4; mu++) {
+        uint32_t key[2];
+        stream_key(seed, 0, (uint32_t)(mu + 1), TAG_HOT, key);
+#pragma omp parallel for
+        for (long s = 0; s < L.V; s++) {
+            M3 m;
+            for (int k = 0; k < 9; k++) {
+                double u0, u1;
+                site_uniform_pair(key, (uint64_t)s, (uint32_t)k, &u0, &u1);
+                m.a[k % 3][k / 3] = cd(u0 - 0.5, u1 - 0.5);
+            }
+            setU(U, L, mu, s, reunitarize(m));
+        }
+    }
+}
+
+// Gaussian momenta: per global site one stream keyed (seed, sweep, mu+1, tag GAUSS); the 8
+// coefficients consume 4 Box-Muller (value, spare) pairs (TA_gaugefields_4D_MPILattice.jl:157-193,
+// test/MPIJACCtest/random_fields_site_rng.jl:22-42)
+void orc_gaussian_momenta(double* P, const int* dims, uint64_t seed, uint64_t sweep, double sigma) {
+    Lat L(dims);
+    for (int mu = 0; mu < 4; mu++) {
+        uint32_t key[2];
+        stream_key(seed, sweep, (uint32_t)(mu + 1), TAG_GAUSS, key);
+#pragma omp parallel for
+        for (long s = 0; s < L.V; s++) {
+            double* p = P + ((long)mu * L.V + s) * 8;
+            for (int k = 0; k < 4; k++) {
+                double u0, u1;
+                site_uniform_pair(key, (uint64_t)s, (uint32_t)k, &u0, &u1);
+                double r = std::sqrt(-2.0 * std::log(1.0 - u0));
+                double th = 2.0 * M_PI * u1;
+                p[2 * k] = sigma * r * std::cos(th);
+                p[2 * k + 1] = sigma * r * std::sin(th);
+            }
+        }
+    }
+}
+
+void orc_reunitarize(double* U, const int* dims) {
+    Lat L(dims);
+    for (int mu = 0; mu < 4; mu++) for (long s = 0; s < L.V; s++) setU(U, L, mu, s, reunitarize(getU(U, L, mu, s)));
+}
+
+// ----------------------------------------------------------------------------- observables
+
+// calculate_Plaquette (src/AbstractGaugefields.jl:2684-2699): sum_{x,mu<nu} Re tr P_munu, un-normalised
+double orc_plaquette_sum(const double* U, const int* dims) {
+    Lat L(dims);
+    double tot = 0.0;
+#pragma omp parallel for reduction(+ : tot)
+    for (long s = 0; s < L.V; s++) {
+        int x[4];
+        L.coord(s, x);
+        double acc = 0.0;
+        for (int mu = 0; mu < 4; mu++)
+            for (int nu = mu + 1; nu < 4; nu++) {
+                Step pl[4] = {{mu, 1}, {nu, 1}, {mu, -1}, {nu, -1}};
+                acc += trace(path_product(U, L, x, pl, 4)).real();
+            }
+        tot += acc;
+    }
+    return tot;
+}
+
+// p*p (src/4D/TA_gaugefields_4D_serial.jl:106-129 summed over directions, src/TA_Gaugefields.jl:127-137)
+double orc_momentum_norm2(const double* P, const int* dims) {
+    Lat L(dims);
+    double tot = 0.0;
+    long n = 4 * L.V * 8;
+#pragma omp parallel for reduction(+ : tot)
+    for (long i = 0; i < n; i++) tot += P[i] * P[i];
+    return tot;
+}
+
+// md_hamiltonian (src/molecular_dynamics.jl:494-505) for the Wilson action pushed as beta/2 * (plaq + plaq')
+double orc_hamiltonian(const double* U, const double* P, const int* dims, double beta) {
+    return -(beta / 3.0) * orc_plaquette_sum(U, dims) + 0.5 * orc_momentum_norm2(P, dims);
+}
+
+// Polyakov loop in the t direction (src/AbstractGaugefields.jl:2929-2956): sum over spatial sites of tr prod_t U_4 / (NX NY NZ)
+void orc_polyakov(const double* U, const int* dims, double* out2) {
+    Lat L(dims);
+    cd tot = 0.0;
+    for (int z = 0; z < L.n[2]; z++) for (int y = 0; y < L.n[1]; y++) for (int x = 0; x < L.n[0]; x++) {
+        M3 r = ident3();
+        for (int t = 0; t < L.n[3]; t++) { int c[4] = {x, y, z, t}; r = mul(r, getU(U, L, 3, L.idx(c))); }
+        tot += trace(r);
+    }
+    tot /= (double)((long)L.n[0] * L.n[1] * L.n[2]);
+    out2[0] = tot.real(); out2[1] = tot.imag();
+}
+
+// clover energy density (samples/measurements/energydensity.jl:4-78)
+double orc_energy_density_clover(const double* U, const int* dims) {
+    Lat L(dims);
+    double tot = 0.0;
+#pragma omp parallel for reduction(+ : tot)
+    for (long s = 0; s < L.V; s++) {
+        int x[4];
+        L.coord(s, x);
+        double acc = 0.0;
+        for (int mu = 0; mu < 4; mu++)
+            for (int nu = 0; nu < 4; nu++) {
+                if (mu == nu) continue;
+                Step l1[4] = {{mu, 1}, {nu, 1}, {mu, -1}, {nu, -1}};
+                Step l2[4] = {{nu, 1}, {mu, -1}, {nu, -1}, {mu, 1}};
+                Step l3[4] = {{nu, -1}, {mu, 1}, {nu, 1}, {mu, -1}};
+                Step l4[4] = {{mu, -1}, {nu, -1}, {mu, 1}, {nu, 1}};
+                M3 w = add(add(path_product(U, L, x, l1, 4), path_product(U, L, x, l2, 4)), add(path_product(U, L, x, l3, 4), path_product(U, L, x, l4, 4)));
+                M3 g = ta_matrix(w);
+                acc += (-trace(mul(g, g)) / 2.0).real();
+            }
+        tot += acc;
+    }
+    return tot / ((double)L.V * 16.0);
+}
+
+// ----------------------------------------------------------------------------- force, updates
+
+// md_force! with the plaquette+plaquette' action at coefficient beta/2
+// (src/molecular_dynamics.jl:251-267, src/action/GaugeActions.jl:95-123):
+//   F_mu = -(1/3) * TAcoeffs( U_mu * (beta/2) * sum of 6 staples )
+void orc_force(double* F, const double* U, const int* dims, double beta) {
+    Lat L(dims);
+#pragma omp parallel for
+    for (long s = 0; s < L.V; s++) {
+        int x[4];
+        L.coord(s, x);
+        for (int mu = 0; mu < 4; mu++) {
+            M3 w = scale(beta / 2.0, U_times_Vdag(U, L, x, mu));
+            double c[8];
+            ta_coeffs(w, c);
+            double* f = F + ((long)mu * L.V + s) * 8;
+            for (int a = 0; a < 8; a++) f[a] = (-1.0 / 3.0) * c[a];
+        }
+    }
+}
+
+// add_force!(F, U; plaqonly=true, factor=1) after clear (src/AbstractGaugefields.jl:2717-2762): F_mu = TAcoeffs(U_mu V_mu^dag)
+void orc_flow_force(double* F, const double* U, const int* dims) {
+    Lat L(dims);
+#pragma omp parallel for
+    for (long s = 0; s < L.V; s++) {
+        int x[4];
+        L.coord(s, x);
+        for (int mu = 0; mu < 4; mu++) ta_coeffs(U_times_Vdag(U, L, x, mu), F + ((long)mu * L.V + s) * 8);
+    }
+}
+
+// update_gaugefields! / exp_aF_U! : U_mu <- exp(eps * P_mu) U_mu
+// (src/molecular_dynamics.jl:513-531, src/AbstractGaugefields.jl:2810-2841); route 0 = Taylor, 1 = eigen
+void orc_update_links_route(double* Uout, const double* Uin, const double* P, const int* dims, double eps, int route) {
+    Lat L(dims);
+#pragma omp parallel for
+    for (long s = 0; s < L.V; s++)
+        for (int mu = 0; mu < 4; mu++) {
+            M3 e = exp_ta(P + ((long)mu * L.V + s) * 8, eps, route);
+            setU(Uout, L, mu, s, mul(e, getU(Uin, L, mu, s)));
+        }
+}
+void orc_update_links(double* U, const double* P, const int* dims, double eps) { orc_update_links_route(U, U, P, dims, eps, 0); }
+
+// update_momenta!: P += eps * force(U) (src/molecular_dynamics.jl:539-551)
+void orc_update_momenta(double* P, const double* U, const int* dims, double eps, double beta) {
+    Lat L(dims);
+    std::vector<double> F((size_t)4 * L.V * 8);
+    orc_force(F.data(), U, dims, beta);
+    long n = 4 * L.V * 8;
+#pragma omp parallel for
+    for (long i = 0; i < n; i++) P[i] += eps * F[i];
+}
+
+// md_step! QPQ / PQP (src/molecular_dynamics.jl:604-616); integrator 0 = QPQ, 1 = PQP
+void orc_md_step(double* U, double* P, const int* dims, double beta, double eps, int integrator) {
+    if (integrator == 0) {
+        orc_update_links(U, P, dims, eps / 2);
+        orc_update_momenta(P, U, dims, eps, beta);
+        orc_update_links(U, P, dims, eps / 2);
+    } else {
+        orc_update_momenta(P, U, dims, eps / 2, beta);
+        orc_update_links(U, P, dims, eps);
+        orc_update_momenta(P, U, dims, eps / 2, beta);
+    }
+}
+
+// md_trajectory! with diagnostics (src/molecular_dynamics.jl:712-730): H[0] initial, H[1] final
+void orc_md_trajectory(double* U, double* P, const int* dims, double beta, int steps, double tau, int integrator, double* H) {
+    H[0] = orc_hamiltonian(U, P, dims, beta);
+    double eps = tau / steps;
+    for (int k = 0; k < steps; k++) orc_md_step(U, P, dims, beta, eps, integrator);
+    H[1] = orc_hamiltonian(U, P, dims, beta);
+}
+
+// one Luescher RK3 step of flow! (src/smearing/gradientflow.jl:171-238)
+void orc_flow_step(double* U, const int* dims, double eps) {
+    Lat L(dims);
+    size_t nf = (size_t)4 * L.V * 8, nu = (size_t)4 * L.V * 18;
+    std::vector<double> F0(nf), F1(nf), F2(nf), Ft(nf), W1(nu), W2(nu);
+    orc_flow_force(F0.data(), U, dims);
+    orc_update_links_route(W1.data(), U, F0.data(), dims, -eps / 4, 0);
+    orc_flow_force(F1.data(), W1.data(), dims);
+    for (size_t i = 0; i < nf; i++) Ft[i] = -(8 * eps / 9) * F1[i] + (17 * eps / 36) * F0[i];
+    orc_update_links_route(W2.data(), W1.data(), Ft.data(), dims, 1.0, 0);
+    orc_flow_force(F2.data(), W2.data(), dims);
+    for (size_t i = 0; i < nf; i++) Ft[i] = -(3 * eps / 4) * F2[i] + (8 * eps / 9) * F1[i] - (17 * eps / 36) * F0[i];
+    orc_update_links_route(U, W2.data(), Ft.data(), dims, 1.0, 0);
+}
+
+// ----------------------------------------------------------------------------- single-matrix probes (unit tests)
+
+void orc_exp_ta(const double* c8, double t, int route, double* out18) {
+    M3 e = exp_ta(c8, t, route);
+    for (int j = 0; j < 3; j++) for (int i = 0; i < 3; i++) { out18[2 * (i + 3 * j)] = e.a[i][j].real(); out18[2 * (i + 3 * j) + 1] = e.a[i][j].imag(); }
+}
+void orc_ta_coeffs(const double* m18, double* c8) {
+    M3 m;
+    for (int j = 0; j < 3; j++) for (int i = 0; i < 3; i++) m.a[i][j] = cd(m18[2 * (i + 3 * j)], m18[2 * (i + 3 * j) + 1]);
+    ta_coeffs(m, c8);
+}
+void orc_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) { philox4x32_10(ctr, key, out); }
+void orc_staple_sum(double* V, const double* U, const int* dims) {
+    Lat L(dims);
+    for (long s = 0; s < L.V; s++) {
+        int x[4];
+        L.coord(s, x);
+        for (int mu = 0; mu < 4; mu++) setU(V, L, mu, s, staple_sum(U, L, x, mu));
+    }
+}
+
+}  // extern "C"

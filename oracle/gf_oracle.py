@@ -1,0 +1,193 @@
+"""ctypes binding of the CPU oracle (oracle/gf_oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  The product package
+(gaugefields.jl_b200/) never imports this module.
+
+Arrays use the reference's host layout (src/API.jl:516-529):
+  U : complex128, shape (4, NT, NZ, NY, NX, 3, 3) C-order with the LAST TWO axes
+      being (column j, row i)  == Julia ComplexF64[3,3,NX,NY,NZ,NT] per direction
+  P : float64,   shape (4, NT, NZ, NY, NX, 8)    == Julia Float64[8,1,NX,NY,NZ,NT]
+`dims` is always (NX, NY, NZ, NT).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libgforacle.so")
+    src = os.path.join(_HERE, "gf_oracle.cpp")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libgforacle.so"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "libgforacle.so")
+        if not os.path.exists(so):
+            build()
+        _LIB = ctypes.CDLL(so)
+        _LIB.orc_plaquette_sum.restype = ctypes.c_double
+        _LIB.orc_momentum_norm2.restype = ctypes.c_double
+        _LIB.orc_hamiltonian.restype = ctypes.c_double
+        _LIB.orc_energy_density_clover.restype = ctypes.c_double
+    return _LIB
+
+
+def _dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def _dims(dims):
+    return (ctypes.c_int * 4)(*[int(d) for d in dims])
+
+
+def u_shape(dims):
+    nx, ny, nz, nt = dims
+    return (4, nt, nz, ny, nx, 3, 3)
+
+
+def p_shape(dims):
+    nx, ny, nz, nt = dims
+    return (4, nt, nz, ny, nx, 8)
+
+
+def new_u(dims):
+    return np.zeros(u_shape(dims), dtype=np.complex128)
+
+
+def new_p(dims):
+    return np.zeros(p_shape(dims), dtype=np.float64)
+
+
+def mats(U):
+    """View with math indexing [..., i, j] (row, column)."""
+    return np.swapaxes(U, -1, -2)
+
+
+def set_cold(dims):
+    U = new_u(dims)
+    lib().orc_set_cold(_dp(U), _dims(dims))
+    return U
+
+
+def hot_start_stable123(dims):
+    U = new_u(dims)
+    lib().orc_hot_start_stable123(_dp(U), _dims(dims))
+    return U
+
+
+def hot_start_philox(dims, seed):
+    U = new_u(dims)
+    lib().orc_hot_start_philox(_dp(U), _dims(dims), ctypes.c_uint64(seed))
+    return U
+
+
+def gaussian_momenta(dims, seed, sweep, sigma=1.0):
+    P = new_p(dims)
+    lib().orc_gaussian_momenta(_dp(P), _dims(dims), ctypes.c_uint64(seed), ctypes.c_uint64(sweep), ctypes.c_double(sigma))
+    return P
+
+
+def reunitarize(U, dims):
+    lib().orc_reunitarize(_dp(U), _dims(dims))
+    return U
+
+
+def plaquette_sum(U, dims):
+    return lib().orc_plaquette_sum(_dp(U), _dims(dims))
+
+
+def plaquette(U, dims):
+    return plaquette_sum(U, dims) / (6.0 * np.prod(dims) * 3.0)
+
+
+def momentum_norm2(P, dims):
+    return lib().orc_momentum_norm2(_dp(P), _dims(dims))
+
+
+def hamiltonian(U, P, dims, beta):
+    return lib().orc_hamiltonian(_dp(U), _dp(P), _dims(dims), ctypes.c_double(beta))
+
+
+def polyakov(U, dims):
+    out = np.zeros(2)
+    lib().orc_polyakov(_dp(U), _dims(dims), _dp(out))
+    return complex(out[0], out[1])
+
+
+def energy_density_clover(U, dims):
+    return lib().orc_energy_density_clover(_dp(U), _dims(dims))
+
+
+def force(U, dims, beta):
+    F = new_p(dims)
+    lib().orc_force(_dp(F), _dp(U), _dims(dims), ctypes.c_double(beta))
+    return F
+
+
+def flow_force(U, dims):
+    F = new_p(dims)
+    lib().orc_flow_force(_dp(F), _dp(U), _dims(dims))
+    return F
+
+
+def update_links(U, P, dims, eps, route=0):
+    out = np.empty_like(U)
+    lib().orc_update_links_route(_dp(out), _dp(U), _dp(P), _dims(dims), ctypes.c_double(eps), ctypes.c_int(route))
+    return out
+
+
+def update_momenta(P, U, dims, eps, beta):
+    lib().orc_update_momenta(_dp(P), _dp(U), _dims(dims), ctypes.c_double(eps), ctypes.c_double(beta))
+    return P
+
+
+def md_step(U, P, dims, beta, eps, integrator=0):
+    lib().orc_md_step(_dp(U), _dp(P), _dims(dims), ctypes.c_double(beta), ctypes.c_double(eps), ctypes.c_int(integrator))
+
+
+def md_trajectory(U, P, dims, beta, steps, tau=1.0, integrator=0):
+    H = np.zeros(2)
+    lib().orc_md_trajectory(_dp(U), _dp(P), _dims(dims), ctypes.c_double(beta), ctypes.c_int(steps), ctypes.c_double(tau), ctypes.c_int(integrator), _dp(H))
+    return H[0], H[1]
+
+
+def flow_step(U, dims, eps):
+    lib().orc_flow_step(_dp(U), _dims(dims), ctypes.c_double(eps))
+
+
+def exp_ta(c8, t=1.0, route=0):
+    c8 = np.ascontiguousarray(c8, dtype=np.float64)
+    out = np.zeros((3, 3), dtype=np.complex128)
+    lib().orc_exp_ta(_dp(c8), ctypes.c_double(t), ctypes.c_int(route), _dp(out))
+    return out.T.copy()  # stored column-major -> math [i, j]
+
+
+def ta_coeffs(m):
+    buf = np.ascontiguousarray(np.asarray(m, dtype=np.complex128).T)
+    c = np.zeros(8)
+    lib().orc_ta_coeffs(_dp(buf), _dp(c))
+    return c
+
+
+def philox(ctr, key):
+    c = (ctypes.c_uint32 * 4)(*ctr)
+    k = (ctypes.c_uint32 * 2)(*key)
+    o = (ctypes.c_uint32 * 4)()
+    lib().orc_philox(c, k, o)
+    return [int(v) for v in o]
+
+
+def staple_sum(U, dims):
+    V = np.empty_like(U)
+    lib().orc_staple_sum(_dp(V), _dp(U), _dims(dims))
+    return V
