@@ -1,0 +1,878 @@
+// api.cu -- the extern "C" boundary of libgfb200.so (declared in include/gfb200.h).
+//
+// Host-side orchestration only: handle management, host<->device layout conversion, t-slab halo
+// exchange over NCCL, deterministic scalar reductions and the integrator loops that string the
+// kernels of kernels.cu / stout.cu together.  No CPU fallback exists: without a usable GPU every
+// entry point fails with GFB_ERR_NODEVICE / GFB_ERR_CUDA.
+#include <cmath>
+#include <cstring>
+
+#include "gfb_internal.h"
+
+namespace gfb {
+
+static std::string g_init_error;
+
+int fail(gfb_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    else g_init_error = msg;
+    return code;
+}
+
+Geom make_geom(const gfb_ctx* ctx, int nx, int ny, int nz, int nt, int slab_global_index) {
+    Geom g;
+    const int G = ctx->nslabs_total;
+    g.nx = nx; g.ny = ny; g.nz = nz;
+    g.tloc = nt / G;
+    g.v3 = nx * ny * nz;
+    g.nt = nt;
+    g.t0 = slab_global_index * g.tloc;
+    if (G > 1) {
+        g.t_up_wrap = g.tloc;
+        g.t_dn_wrap = g.tloc + 1;
+        g.nslots = g.tloc + 2;
+    } else {
+        g.t_up_wrap = 0;
+        g.t_dn_wrap = g.tloc - 1;
+        g.nslots = g.tloc;
+    }
+    // z-chunk of the traversal: largest divisor of nz whose xy*zc slab of links stays <= 24 MiB, so the
+    // t+-1 neighbours of a chunk are still L2-resident when the sweep comes back to them
+    const double budget = 24.0 * 1024 * 1024;
+    int zc = nz;
+    while (zc > 1 && (double)nx * ny * zc * 576.0 > budget) {
+        int d = zc - 1;
+        while (d > 1 && nz % d != 0) d--;
+        zc = d;
+    }
+    g.zc = zc;
+    return g;
+}
+
+static int check_dims(gfb_ctx* ctx, int nx, int ny, int nz, int nt) {
+    if (!ctx) return fail(nullptr, GFB_ERR_ARG, "null context");
+    if (nx <= 0 || ny <= 0 || nz <= 0 || nt <= 0) return fail(ctx, GFB_ERR_ARG, "all lattice extents must be positive");
+    if (nt % ctx->nslabs_total != 0) return fail(ctx, GFB_ERR_ARG, "NT must be divisible by the number of GPUs (t-slab decomposition)");
+    if (ctx->nslabs_total > 1 && nt / ctx->nslabs_total < 2) return fail(ctx, GFB_ERR_ARG, "each t-slab needs at least 2 time-slices");
+    if ((double)nx * ny * nz > 2.0e9 / 36.0) return fail(ctx, GFB_ERR_ARG, "spatial volume too large for 32-bit slice indexing");
+    return GFB_OK;
+}
+
+static int ensure_partial(gfb_ctx* ctx, Slab& s, size_t n) {
+    if (s.partial_cap >= n) return GFB_OK;
+    GFB_CUDA(ctx, cudaSetDevice(s.device));
+    if (s.d_partial) GFB_CUDA(ctx, cudaFree(s.d_partial));
+    s.d_partial = nullptr;
+    GFB_CUDA(ctx, cudaMalloc(&s.d_partial, n * sizeof(double)));
+    s.partial_cap = n;
+    return GFB_OK;
+}
+static int ensure_staging(gfb_ctx* ctx, Slab& s, size_t bytes) {
+    if (s.staging_cap >= bytes) return GFB_OK;
+    GFB_CUDA(ctx, cudaSetDevice(s.device));
+    if (s.d_staging) GFB_CUDA(ctx, cudaFree(s.d_staging));
+    s.d_staging = nullptr;
+    GFB_CUDA(ctx, cudaMalloc(&s.d_staging, bytes));
+    s.staging_cap = bytes;
+    return GFB_OK;
+}
+
+static int init_slab(gfb_ctx* ctx, Slab& s) {
+    GFB_CUDA(ctx, cudaSetDevice(s.device));
+    GFB_CUDA(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    GFB_CUDA(ctx, cudaStreamCreateWithFlags(&s.comm_stream, cudaStreamNonBlocking));
+    GFB_CUDA(ctx, cudaEventCreateWithFlags(&s.ev_a, cudaEventDisableTiming));
+    GFB_CUDA(ctx, cudaEventCreateWithFlags(&s.ev_b, cudaEventDisableTiming));
+    GFB_CUDA(ctx, cudaEventCreateWithFlags(&s.ev_c, cudaEventDisableTiming));
+    GFB_CUDA(ctx, cudaEventCreate(&s.ev_tic));
+    GFB_CUDA(ctx, cudaEventCreate(&s.ev_toc));
+    GFB_CUDA(ctx, cudaMalloc(&s.d_result, 64 * sizeof(double)));
+    GFB_CUDA(ctx, cudaMallocHost(&s.h_result, 64 * sizeof(double)));
+    return GFB_OK;
+}
+
+// Sum one scalar per local slab (already in d_result[slot]) over all slabs of all ranks, in slab order.
+static int gather_scalars(gfb_ctx* ctx, int nslots, double* out) {
+    const int G = ctx->nslabs_total;
+    for (int k = 0; k < nslots; k++) out[k] = 0.0;
+    if (!ctx->distributed) {
+        for (auto& s : ctx->slabs) {
+            GFB_CUDA(ctx, cudaSetDevice(s.device));
+            GFB_CUDA(ctx, cudaMemcpyAsync(s.h_result, s.d_result, nslots * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+        }
+        for (auto& s : ctx->slabs) {
+            GFB_CUDA(ctx, cudaSetDevice(s.device));
+            GFB_CUDA(ctx, cudaStreamSynchronize(s.stream));
+            for (int k = 0; k < nslots; k++) out[k] += s.h_result[k];
+        }
+        return GFB_OK;
+    }
+    // one process per GPU: all-gather the per-rank values and add them in rank order on every rank
+    Slab& s = ctx->slabs[0];
+    GFB_CUDA(ctx, cudaSetDevice(s.device));
+    if (nslots * G > 56) return fail(ctx, GFB_ERR_ARG, "too many ranks for the scalar gather area");
+    GFB_NCCL(ctx, ncclAllGather(s.d_result, s.d_result + 8, nslots, ncclDouble, s.nccl, s.stream));
+    GFB_CUDA(ctx, cudaMemcpyAsync(s.h_result, s.d_result + 8, (size_t)nslots * G * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    GFB_CUDA(ctx, cudaStreamSynchronize(s.stream));
+    for (int r = 0; r < G; r++)
+        for (int k = 0; k < nslots; k++) out[k] += s.h_result[r * nslots + k];
+    return GFB_OK;
+}
+
+// t-halo exchange of `buf` (layout of gfb_gauge::d) on the compute streams: slot tloc <- next slab's
+// slice 0, slot tloc+1 <- previous slab's last slice (set_wing_U!/set_halo! in the
+// reference, gaugefields_4D_MPILattice.jl:497-507).
+static int exchange_halo_buffers(gfb_ctx* ctx, const gfb_gauge* g, const std::vector<double2*>& buf, bool on_comm_stream) {
+    const int G = ctx->nslabs_total;
+    if (G == 1) return GFB_OK;
+    const size_t slice = g->slice_elems() * 2;  // doubles
+    const size_t up_count = (size_t)27 * g->nx * g->ny * g->nz * 2;  // the t+1 halo only needs the three spatial links
+    GFB_NCCL(ctx, ncclGroupStart());
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        Slab& s = ctx->slabs[i];
+        cudaStream_t st = on_comm_stream ? s.comm_stream : s.stream;
+        const int prev = (s.index + G - 1) % G, next = (s.index + 1) % G;
+        double* base = reinterpret_cast<double*>(buf[i]);
+        double* first = base;
+        double* last = base + (size_t)(g->tloc - 1) * slice;
+        double* up = base + (size_t)g->tloc * slice;
+        double* dn = base + (size_t)(g->tloc + 1) * slice;
+        GFB_NCCL(ctx, ncclSend(first, up_count, ncclDouble, prev, s.nccl, st));
+        GFB_NCCL(ctx, ncclSend(last, slice, ncclDouble, next, s.nccl, st));
+        GFB_NCCL(ctx, ncclRecv(up, up_count, ncclDouble, next, s.nccl, st));
+        GFB_NCCL(ctx, ncclRecv(dn, slice, ncclDouble, prev, s.nccl, st));
+    }
+    GFB_NCCL(ctx, ncclGroupEnd());
+    return GFB_OK;
+}
+static int ensure_halo(gfb_gauge* g) {
+    if (!g->has_halo || g->halo_valid) return GFB_OK;
+    GFB_CHECK(exchange_halo_buffers(g->ctx, g, g->d, false));
+    g->halo_valid = true;
+    return GFB_OK;
+}
+
+static int alloc_like(gfb_ctx* ctx, const gfb_gauge* g, std::vector<double2*>& out) {
+    out.assign(ctx->slabs.size(), nullptr);
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
+        GFB_CUDA(ctx, cudaMalloc(&out[i], g->elems_per_slab() * sizeof(double2)));
+    }
+    return GFB_OK;
+}
+
+}  // namespace gfb
+
+using namespace gfb;
+
+// workspaces owned by a gauge handle (double buffer for the fused updates, flow field Z)
+struct gfb_gauge_ws {
+    std::vector<double2*> alt;
+    std::vector<double*> z;
+};
+#include <unordered_map>
+static std::unordered_map<const gfb_gauge*, gfb_gauge_ws> g_ws;
+
+static int get_ws(gfb_gauge* g, bool need_alt, bool need_z, gfb_gauge_ws** out) {
+    gfb_ctx* ctx = g->ctx;
+    gfb_gauge_ws& ws = g_ws[g];
+    if (need_alt && ws.alt.empty()) GFB_CHECK(alloc_like(ctx, g, ws.alt));
+    if (need_z && ws.z.empty()) {
+        ws.z.assign(ctx->slabs.size(), nullptr);
+        size_t n = (size_t)g->tloc * 32 * g->nx * g->ny * g->nz;
+        for (size_t i = 0; i < ctx->slabs.size(); i++) {
+            GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
+            GFB_CUDA(ctx, cudaMalloc(&ws.z[i], n * sizeof(double)));
+        }
+    }
+    *out = &ws;
+    return GFB_OK;
+}
+static void free_ws(gfb_gauge* g) {
+    auto it = g_ws.find(g);
+    if (it == g_ws.end()) return;
+    for (size_t i = 0; i < it->second.alt.size(); i++) { cudaSetDevice(g->ctx->slabs[i].device); cudaFree(it->second.alt[i]); }
+    for (size_t i = 0; i < it->second.z.size(); i++) { cudaSetDevice(g->ctx->slabs[i].device); cudaFree(it->second.z[i]); }
+    g_ws.erase(it);
+}
+
+static bool same_shape(const gfb_gauge* a, const gfb_gauge* b) { return a->ctx == b->ctx && a->nx == b->nx && a->ny == b->ny && a->nz == b->nz && a->nt == b->nt; }
+static bool same_shape(const gfb_gauge* a, const gfb_mom* b) { return a->ctx == b->ctx && a->nx == b->nx && a->ny == b->ny && a->nz == b->nz && a->nt == b->nt; }
+static bool same_shape(const gfb_mom* a, const gfb_mom* b) { return a->ctx == b->ctx && a->nx == b->nx && a->ny == b->ny && a->nz == b->nz && a->nt == b->nt; }
+static Geom geom_of(const gfb_gauge* g, size_t i) { return make_geom(g->ctx, g->nx, g->ny, g->nz, g->nt, g->ctx->slabs[i].index); }
+static Geom geom_of(const gfb_mom* p, size_t i) { return make_geom(p->ctx, p->nx, p->ny, p->nz, p->nt, p->ctx->slabs[i].index); }
+static int post_launch(gfb_ctx* ctx, int nlaunch = 1) {
+    ctx->launches += nlaunch;
+    GFB_CUDA(ctx, cudaGetLastError());
+    return GFB_OK;
+}
+
+extern "C" {
+
+int gfb_version(void) { return 100; }
+
+const char* gfb_last_error(const gfb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
+
+int gfb_init(int ngpu, const int* devices, gfb_ctx** out) {
+    if (!out) return fail(nullptr, GFB_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (ngpu <= 0) return fail(nullptr, GFB_ERR_ARG, "ngpu must be positive");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(nullptr, GFB_ERR_NODEVICE, std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (ngpu > ndev) return fail(nullptr, GFB_ERR_ARG, "more GPUs requested than visible");
+    gfb_ctx* ctx = new gfb_ctx();
+    ctx->nslabs_total = ngpu;
+    ctx->distributed = false;
+    ctx->slabs.resize(ngpu);
+    std::vector<int> devs(ngpu);
+    for (int i = 0; i < ngpu; i++) {
+        devs[i] = devices ? devices[i] : i;
+        ctx->slabs[i].device = devs[i];
+        ctx->slabs[i].index = i;
+    }
+    for (auto& s : ctx->slabs) {
+        int st = init_slab(ctx, s);
+        if (st != GFB_OK) { g_init_error = ctx->err; delete ctx; return st; }
+    }
+    if (ngpu > 1) {
+        std::vector<ncclComm_t> comms(ngpu);
+        ncclResult_t r = ncclCommInitAll(comms.data(), ngpu, devs.data());
+        if (r != ncclSuccess) { g_init_error = std::string("ncclCommInitAll: ") + ncclGetErrorString(r); delete ctx; return GFB_ERR_NCCL; }
+        for (int i = 0; i < ngpu; i++) ctx->slabs[i].nccl = comms[i];
+    }
+    *out = ctx;
+    return GFB_OK;
+}
+
+int gfb_nccl_unique_id(char* out128) {
+    if (!out128) return fail(nullptr, GFB_ERR_ARG, "out128 is null");
+    ncclUniqueId id;
+    ncclResult_t r = ncclGetUniqueId(&id);
+    if (r != ncclSuccess) return fail(nullptr, GFB_ERR_NCCL, std::string("ncclGetUniqueId: ") + ncclGetErrorString(r));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    std::memcpy(out128, &id, 128);
+    return GFB_OK;
+}
+
+int gfb_init_rank(int rank, int nranks, const char* id128, int device, gfb_ctx** out) {
+    if (!out) return fail(nullptr, GFB_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (nranks <= 0 || rank < 0 || rank >= nranks) return fail(nullptr, GFB_ERR_ARG, "invalid rank/nranks");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(nullptr, GFB_ERR_NODEVICE, std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, GFB_ERR_ARG, "invalid device index");
+    gfb_ctx* ctx = new gfb_ctx();
+    ctx->nslabs_total = nranks;
+    ctx->distributed = nranks > 1;
+    ctx->slabs.resize(1);
+    ctx->slabs[0].device = device;
+    ctx->slabs[0].index = rank;
+    int st = init_slab(ctx, ctx->slabs[0]);
+    if (st != GFB_OK) { g_init_error = ctx->err; delete ctx; return st; }
+    if (nranks > 1) {
+        if (!id128) { delete ctx; return fail(nullptr, GFB_ERR_ARG, "id128 is null"); }
+        ncclUniqueId id;
+        std::memcpy(&id, id128, 128);
+        ncclResult_t r = ncclCommInitRank(&ctx->slabs[0].nccl, nranks, id, rank);
+        if (r != ncclSuccess) { g_init_error = std::string("ncclCommInitRank: ") + ncclGetErrorString(r); delete ctx; return GFB_ERR_NCCL; }
+    }
+    *out = ctx;
+    return GFB_OK;
+}
+
+int gfb_finalize(gfb_ctx* ctx) {
+    if (!ctx) return GFB_OK;
+    for (auto& s : ctx->slabs) {
+        cudaSetDevice(s.device);
+        cudaDeviceSynchronize();
+        if (s.nccl) ncclCommDestroy(s.nccl);
+        if (s.d_partial) cudaFree(s.d_partial);
+        if (s.d_result) cudaFree(s.d_result);
+        if (s.h_result) cudaFreeHost(s.h_result);
+        if (s.d_staging) cudaFree(s.d_staging);
+        cudaEventDestroy(s.ev_a); cudaEventDestroy(s.ev_b); cudaEventDestroy(s.ev_c);
+        cudaEventDestroy(s.ev_tic); cudaEventDestroy(s.ev_toc);
+        cudaStreamDestroy(s.stream); cudaStreamDestroy(s.comm_stream);
+    }
+    delete ctx;
+    return GFB_OK;
+}
+
+int gfb_sync(gfb_ctx* ctx) {
+    if (!ctx) return fail(nullptr, GFB_ERR_ARG, "null context");
+    for (auto& s : ctx->slabs) {
+        GFB_CUDA(ctx, cudaSetDevice(s.device));
+        GFB_CUDA(ctx, cudaStreamSynchronize(s.stream));
+        GFB_CUDA(ctx, cudaStreamSynchronize(s.comm_stream));
+    }
+    return GFB_OK;
+}
+
+int gfb_num_slabs(const gfb_ctx* ctx, int* local, int* total) {
+    if (!ctx) return GFB_ERR_ARG;
+    if (local) *local = (int)ctx->slabs.size();
+    if (total) *total = ctx->nslabs_total;
+    return GFB_OK;
+}
+
+int gfb_timer_tic(gfb_ctx* ctx) {
+    if (!ctx) return GFB_ERR_ARG;
+    for (auto& s : ctx->slabs) {
+        GFB_CUDA(ctx, cudaSetDevice(s.device));
+        GFB_CUDA(ctx, cudaEventRecord(s.ev_tic, s.stream));
+    }
+    return GFB_OK;
+}
+int gfb_timer_toc(gfb_ctx* ctx, double* ms) {
+    if (!ctx || !ms) return GFB_ERR_ARG;
+    double worst = 0.0;
+    for (auto& s : ctx->slabs) {
+        GFB_CUDA(ctx, cudaSetDevice(s.device));
+        GFB_CUDA(ctx, cudaEventRecord(s.ev_toc, s.stream));
+    }
+    for (auto& s : ctx->slabs) {
+        GFB_CUDA(ctx, cudaSetDevice(s.device));
+        GFB_CUDA(ctx, cudaEventSynchronize(s.ev_toc));
+        float f = 0.f;
+        GFB_CUDA(ctx, cudaEventElapsedTime(&f, s.ev_tic, s.ev_toc));
+        if (f > worst) worst = f;
+    }
+    *ms = worst;
+    return GFB_OK;
+}
+int gfb_kernel_launches(const gfb_ctx* ctx, long long* count) {
+    if (!ctx || !count) return GFB_ERR_ARG;
+    *count = ctx->launches;
+    return GFB_OK;
+}
+int gfb_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return GFB_ERR_ARG;
+    cudaError_t e = cudaMallocHost(ptr, bytes);
+    if (e != cudaSuccess) return fail(nullptr, GFB_ERR_CUDA, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+    return GFB_OK;
+}
+int gfb_host_free(void* ptr) {
+    if (ptr) cudaFreeHost(ptr);
+    return GFB_OK;
+}
+
+// ---- fields -----------------------------------------------------------------------------------
+int gfb_gauge_alloc(gfb_ctx* ctx, int nx, int ny, int nz, int nt, gfb_gauge** out) {
+    if (!out) return fail(ctx, GFB_ERR_ARG, "out is null");
+    *out = nullptr;
+    GFB_CHECK(check_dims(ctx, nx, ny, nz, nt));
+    gfb_gauge* g = new gfb_gauge();
+    g->ctx = ctx; g->nx = nx; g->ny = ny; g->nz = nz; g->nt = nt;
+    g->tloc = nt / ctx->nslabs_total;
+    g->has_halo = ctx->nslabs_total > 1;
+    g->halo_valid = false;
+    int st = alloc_like(ctx, g, g->d);
+    if (st != GFB_OK) { for (auto p : g->d) if (p) cudaFree(p); delete g; return st; }
+    *out = g;
+    return GFB_OK;
+}
+int gfb_gauge_free(gfb_gauge* g) {
+    if (!g) return GFB_OK;
+    free_ws(g);
+    for (size_t i = 0; i < g->d.size(); i++) { cudaSetDevice(g->ctx->slabs[i].device); cudaFree(g->d[i]); }
+    delete g;
+    return GFB_OK;
+}
+int gfb_mom_alloc(gfb_ctx* ctx, int nx, int ny, int nz, int nt, gfb_mom** out) {
+    if (!out) return fail(ctx, GFB_ERR_ARG, "out is null");
+    *out = nullptr;
+    GFB_CHECK(check_dims(ctx, nx, ny, nz, nt));
+    gfb_mom* p = new gfb_mom();
+    p->ctx = ctx; p->nx = nx; p->ny = ny; p->nz = nz; p->nt = nt;
+    p->tloc = nt / ctx->nslabs_total;
+    p->d.assign(ctx->slabs.size(), nullptr);
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
+        GFB_CUDA(ctx, cudaMalloc(&p->d[i], p->elems_per_slab() * sizeof(double)));
+        GFB_CUDA(ctx, cudaMemsetAsync(p->d[i], 0, p->elems_per_slab() * sizeof(double), ctx->slabs[i].stream));
+    }
+    *out = p;
+    return GFB_OK;
+}
+int gfb_mom_free(gfb_mom* p) {
+    if (!p) return GFB_OK;
+    for (size_t i = 0; i < p->d.size(); i++) { cudaSetDevice(p->ctx->slabs[i].device); cudaFree(p->d[i]); }
+    delete p;
+    return GFB_OK;
+}
+
+int gfb_gauge_upload(gfb_gauge* g, int mu, const double* host) {
+    if (!g || !host) return fail(g ? g->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = g->ctx;
+    if (mu < 0 || mu > 3) return fail(ctx, GFB_ERR_ARG, "mu must be in 0..3");
+    const size_t v3 = (size_t)g->nx * g->ny * g->nz;
+    const size_t bytes = v3 * g->tloc * 9 * sizeof(double2);
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        Slab& s = ctx->slabs[i];
+        GFB_CHECK(ensure_staging(ctx, s, bytes));
+        GFB_CUDA(ctx, cudaSetDevice(s.device));
+        Geom geo = geom_of(g, i);
+        const double* src = host + (size_t)geo.t0 * v3 * 18;
+        GFB_CUDA(ctx, cudaMemcpyAsync(s.d_staging, src, bytes, cudaMemcpyHostToDevice, s.stream));
+        launch_links_from_host_layout(s.stream, geo, mu, reinterpret_cast<const double2*>(s.d_staging), g->d[i]);
+        GFB_CHECK(post_launch(ctx));
+    }
+    g->halo_valid = false;
+    return GFB_OK;
+}
+int gfb_gauge_download(const gfb_gauge* g, int mu, double* host) {
+    if (!g || !host) return fail(g ? g->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = g->ctx;
+    if (mu < 0 || mu > 3) return fail(ctx, GFB_ERR_ARG, "mu must be in 0..3");
+    const size_t v3 = (size_t)g->nx * g->ny * g->nz;
+    const size_t bytes = v3 * g->tloc * 9 * sizeof(double2);
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        Slab& s = ctx->slabs[i];
+        GFB_CHECK(ensure_staging(ctx, s, bytes));
+        GFB_CUDA(ctx, cudaSetDevice(s.device));
+        Geom geo = geom_of(g, i);
+        launch_links_to_host_layout(s.stream, geo, mu, g->d[i], reinterpret_cast<double2*>(s.d_staging));
+        GFB_CHECK(post_launch(ctx));
+        double* dst = host + (size_t)geo.t0 * v3 * 18;
+        GFB_CUDA(ctx, cudaMemcpyAsync(dst, s.d_staging, bytes, cudaMemcpyDeviceToHost, s.stream));
+    }
+    for (auto& s : ctx->slabs) { GFB_CUDA(ctx, cudaSetDevice(s.device)); GFB_CUDA(ctx, cudaStreamSynchronize(s.stream)); }
+    return GFB_OK;
+}
+int gfb_mom_upload(gfb_mom* p, int mu, const double* host) {
+    if (!p || !host) return fail(p ? p->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = p->ctx;
+    if (mu < 0 || mu > 3) return fail(ctx, GFB_ERR_ARG, "mu must be in 0..3");
+    const size_t v3 = (size_t)p->nx * p->ny * p->nz;
+    const size_t bytes = v3 * p->tloc * 8 * sizeof(double);
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        Slab& s = ctx->slabs[i];
+        GFB_CHECK(ensure_staging(ctx, s, bytes));
+        GFB_CUDA(ctx, cudaSetDevice(s.device));
+        Geom geo = geom_of(p, i);
+        const double* src = host + (size_t)geo.t0 * v3 * 8;
+        GFB_CUDA(ctx, cudaMemcpyAsync(s.d_staging, src, bytes, cudaMemcpyHostToDevice, s.stream));
+        launch_mom_from_host_layout(s.stream, geo, mu, reinterpret_cast<const double*>(s.d_staging), p->d[i]);
+        GFB_CHECK(post_launch(ctx));
+    }
+    return GFB_OK;
+}
+int gfb_mom_download(const gfb_mom* p, int mu, double* host) {
+    if (!p || !host) return fail(p ? p->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = p->ctx;
+    if (mu < 0 || mu > 3) return fail(ctx, GFB_ERR_ARG, "mu must be in 0..3");
+    const size_t v3 = (size_t)p->nx * p->ny * p->nz;
+    const size_t bytes = v3 * p->tloc * 8 * sizeof(double);
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        Slab& s = ctx->slabs[i];
+        GFB_CHECK(ensure_staging(ctx, s, bytes));
+        GFB_CUDA(ctx, cudaSetDevice(s.device));
+        Geom geo = geom_of(p, i);
+        launch_mom_to_host_layout(s.stream, geo, mu, p->d[i], reinterpret_cast<double*>(s.d_staging));
+        GFB_CHECK(post_launch(ctx));
+        double* dst = host + (size_t)geo.t0 * v3 * 8;
+        GFB_CUDA(ctx, cudaMemcpyAsync(dst, s.d_staging, bytes, cudaMemcpyDeviceToHost, s.stream));
+    }
+    for (auto& s : ctx->slabs) { GFB_CUDA(ctx, cudaSetDevice(s.device)); GFB_CUDA(ctx, cudaStreamSynchronize(s.stream)); }
+    return GFB_OK;
+}
+
+int gfb_gauge_copy(gfb_gauge* dst, const gfb_gauge* src) {
+    if (!dst || !src) return fail(dst ? dst->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = dst->ctx;
+    if (!same_shape(dst, src)) return fail(ctx, GFB_ERR_ARG, "destination and source lattice sizes differ");
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
+        GFB_CUDA(ctx, cudaMemcpyAsync(dst->d[i], src->d[i], src->elems_per_slab() * sizeof(double2), cudaMemcpyDeviceToDevice, ctx->slabs[i].stream));
+    }
+    dst->halo_valid = src->halo_valid;
+    return GFB_OK;
+}
+int gfb_mom_copy(gfb_mom* dst, const gfb_mom* src) {
+    if (!dst || !src) return fail(dst ? dst->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = dst->ctx;
+    if (!same_shape(dst, src)) return fail(ctx, GFB_ERR_ARG, "destination and source lattice sizes differ");
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
+        GFB_CUDA(ctx, cudaMemcpyAsync(dst->d[i], src->d[i], src->elems_per_slab() * sizeof(double), cudaMemcpyDeviceToDevice, ctx->slabs[i].stream));
+    }
+    return GFB_OK;
+}
+int gfb_mom_zero(gfb_mom* p) {
+    if (!p) return fail(nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = p->ctx;
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
+        GFB_CUDA(ctx, cudaMemsetAsync(p->d[i], 0, p->elems_per_slab() * sizeof(double), ctx->slabs[i].stream));
+    }
+    return GFB_OK;
+}
+int gfb_mom_axpy(gfb_mom* p, double t, const gfb_mom* f) {
+    if (!p || !f) return fail(p ? p->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = p->ctx;
+    if (!same_shape(p, f)) return fail(ctx, GFB_ERR_ARG, "momentum fields differ in shape");
+    if (!std::isfinite(t)) return fail(ctx, GFB_ERR_ARG, "the step size must be finite");
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
+        launch_axpy(ctx->slabs[i].stream, p->d[i], t, f->d[i], p->elems_per_slab());
+        GFB_CHECK(post_launch(ctx));
+    }
+    return GFB_OK;
+}
+
+// ---- initial fields -----------------------------------------------------------------------------
+int gfb_set_cold(gfb_gauge* g) {
+    if (!g) return fail(nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = g->ctx;
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
+        launch_set_cold(ctx->slabs[i].stream, geom_of(g, i), g->d[i]);
+        GFB_CHECK(post_launch(ctx));
+    }
+    g->halo_valid = false;
+    return GFB_OK;
+}
+int gfb_set_hot(gfb_gauge* g, uint64_t seed, int rng_alg) {
+    if (!g) return fail(nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = g->ctx;
+    if (rng_alg != GFB_PHILOX4X32) return fail(ctx, GFB_ERR_ARG, "only the Philox4x32 site RNG is implemented");
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
+        launch_set_hot(ctx->slabs[i].stream, geom_of(g, i), g->d[i], seed);
+        GFB_CHECK(post_launch(ctx));
+    }
+    g->halo_valid = false;
+    return GFB_OK;
+}
+int gfb_gaussian_momenta(gfb_mom* p, uint64_t seed, uint64_t sweep, double sigma, int rng_alg) {
+    if (!p) return fail(nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = p->ctx;
+    if (rng_alg != GFB_PHILOX4X32) return fail(ctx, GFB_ERR_ARG, "only the Philox4x32 site RNG is implemented");
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
+        launch_gaussian(ctx->slabs[i].stream, geom_of(p, i), p->d[i], seed, sweep, sigma);
+        GFB_CHECK(post_launch(ctx));
+    }
+    return GFB_OK;
+}
+int gfb_reunitarize(gfb_gauge* g) {
+    if (!g) return fail(nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = g->ctx;
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
+        launch_reunitarize(ctx->slabs[i].stream, geom_of(g, i), g->d[i]);
+        GFB_CHECK(post_launch(ctx));
+    }
+    g->halo_valid = false;
+    return GFB_OK;
+}
+
+// ---- observables ----------------------------------------------------------------------------------
+static int plaquette_partial(gfb_gauge* g, int slot) {
+    gfb_ctx* ctx = g->ctx;
+    GFB_CHECK(ensure_halo(g));
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        Slab& s = ctx->slabs[i];
+        Geom geo = geom_of(g, i);
+        GFB_CHECK(ensure_partial(ctx, s, (size_t)plaquette_blocks(geo) * 2 + 16));
+        GFB_CUDA(ctx, cudaSetDevice(s.device));
+        int nb = 0;
+        launch_plaquette(s.stream, geo, g->d[i], s.d_partial, &nb);
+        launch_final_reduce(s.stream, s.d_partial, nb, s.d_result + slot);
+        GFB_CHECK(post_launch(ctx, 2));
+    }
+    return GFB_OK;
+}
+static int kinetic_partial(gfb_mom* p, int slot) {
+    gfb_ctx* ctx = p->ctx;
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        Slab& s = ctx->slabs[i];
+        GFB_CHECK(ensure_partial(ctx, s, (size_t)sumsq_blocks(p->elems_per_slab()) + 16));
+        GFB_CUDA(ctx, cudaSetDevice(s.device));
+        int nb = 0;
+        launch_sumsq(s.stream, p->d[i], p->elems_per_slab(), s.d_partial, &nb);
+        launch_final_reduce(s.stream, s.d_partial, nb, s.d_result + slot);
+        GFB_CHECK(post_launch(ctx, 2));
+    }
+    return GFB_OK;
+}
+
+int gfb_plaquette_sum(gfb_gauge* g, double* out) {
+    if (!g || !out) return fail(g ? g->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    GFB_CHECK(plaquette_partial(g, 0));
+    return gather_scalars(g->ctx, 1, out);
+}
+int gfb_wilson_action(gfb_gauge* g, double beta, double* out) {
+    double s = 0.0;
+    GFB_CHECK(gfb_plaquette_sum(g, &s));
+    *out = beta * s;
+    return GFB_OK;
+}
+int gfb_kinetic(gfb_mom* p, double* out) {
+    if (!p || !out) return fail(p ? p->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    GFB_CHECK(kinetic_partial(p, 0));
+    return gather_scalars(p->ctx, 1, out);
+}
+int gfb_hamiltonian(gfb_gauge* g, gfb_mom* p, double beta, double* out) {
+    if (!g || !p || !out) return fail(g ? g->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    if (!same_shape(g, p)) return fail(g->ctx, GFB_ERR_ARG, "U and p must have the same lattice");
+    GFB_CHECK(plaquette_partial(g, 0));
+    // the kinetic pass reuses d_partial: stream order keeps the two reductions apart
+    GFB_CHECK(kinetic_partial(p, 1));
+    double v[2];
+    GFB_CHECK(gather_scalars(g->ctx, 2, v));
+    *out = -(beta / 3.0) * v[0] + 0.5 * v[1];
+    return GFB_OK;
+}
+int gfb_energy_density(gfb_gauge* g, int kind, double* out) {
+    if (!g || !out) return fail(g ? g->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = g->ctx;
+    const double V = (double)g->nx * g->ny * g->nz * g->nt;
+    if (kind == GFB_E_PLAQUETTE) {
+        double s = 0.0;
+        GFB_CHECK(gfb_plaquette_sum(g, &s));
+        *out = 2.0 * (18.0 - s / V);
+        return GFB_OK;
+    }
+    if (kind != GFB_E_CLOVER) return fail(ctx, GFB_ERR_ARG, "unknown energy-density kind");
+    GFB_CHECK(ensure_halo(g));
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        Slab& s = ctx->slabs[i];
+        Geom geo = geom_of(g, i);
+        GFB_CHECK(ensure_partial(ctx, s, (size_t)plaquette_blocks(geo) * 2 + 16));
+        GFB_CUDA(ctx, cudaSetDevice(s.device));
+        int nb = 0;
+        launch_clover_energy(s.stream, geo, g->d[i], s.d_partial, &nb);
+        launch_final_reduce(s.stream, s.d_partial, nb, s.d_result);
+        GFB_CHECK(post_launch(ctx, 2));
+    }
+    double v = 0.0;
+    GFB_CHECK(gather_scalars(ctx, 1, &v));
+    *out = v / (V * 16.0);
+    return GFB_OK;
+}
+int gfb_polyakov(gfb_gauge* g, double* out2) {
+    if (!g || !out2) return fail(g ? g->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = g->ctx;
+    if (ctx->nslabs_total != 1) return fail(ctx, GFB_ERR_ARG, "the Polyakov loop is implemented for a single t-slab only");
+    Slab& s = ctx->slabs[0];
+    Geom geo = geom_of(g, 0);
+    GFB_CHECK(ensure_partial(ctx, s, (size_t)plaquette_blocks(geo) * 2 + 16));
+    GFB_CUDA(ctx, cudaSetDevice(s.device));
+    int nb = 0;
+    launch_polyakov(s.stream, geo, g->d[0], s.d_partial, &nb);
+    launch_final_reduce(s.stream, s.d_partial, nb, s.d_result);
+    launch_final_reduce(s.stream, s.d_partial + nb, nb, s.d_result + 1);
+    GFB_CHECK(post_launch(ctx, 3));
+    double v[2];
+    GFB_CHECK(gather_scalars(ctx, 2, v));
+    out2[0] = v[0] / geo.v3;
+    out2[1] = v[1] / geo.v3;
+    return GFB_OK;
+}
+
+// ---- updates -----------------------------------------------------------------------------------------
+// one fused pass over all local slabs: Z' = a*TA(U V^dag) + b*Z ; Uout = exp(c Z') Uin
+static int fused_pass(gfb_gauge* g, const std::vector<double2*>& uin, const std::vector<double2*>* uout, const std::vector<double*>* zin,
+                      const std::vector<double*>* zout, const FusedArgs& fa) {
+    gfb_ctx* ctx = g->ctx;
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        Slab& s = ctx->slabs[i];
+        GFB_CUDA(ctx, cudaSetDevice(s.device));
+        Geom geo = geom_of(g, i);
+        launch_force_fused(s.stream, geo, 0, geo.tloc, uin[i], uout ? (*uout)[i] : nullptr, zin ? (*zin)[i] : nullptr, zout ? (*zout)[i] : nullptr, fa);
+        GFB_CHECK(post_launch(ctx));
+    }
+    return GFB_OK;
+}
+
+int gfb_force(gfb_mom* f, gfb_gauge* g, double beta) {
+    if (!f || !g) return fail(g ? g->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    if (!same_shape(g, f)) return fail(g->ctx, GFB_ERR_ARG, "force and U must have the same lattice");
+    GFB_CHECK(ensure_halo(g));
+    FusedArgs fa;
+    fa.a = -beta / 6.0;  // -(1/NC) * (beta/2)
+    fa.write_z = true;
+    return fused_pass(g, g->d, nullptr, nullptr, &f->d, fa);
+}
+int gfb_flow_force(gfb_mom* f, gfb_gauge* g) {
+    if (!f || !g) return fail(g ? g->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    if (!same_shape(g, f)) return fail(g->ctx, GFB_ERR_ARG, "force and U must have the same lattice");
+    GFB_CHECK(ensure_halo(g));
+    FusedArgs fa;
+    fa.a = 1.0;
+    fa.write_z = true;
+    return fused_pass(g, g->d, nullptr, nullptr, &f->d, fa);
+}
+int gfb_update_momenta(gfb_mom* p, gfb_gauge* g, double eps, double beta) {
+    if (!p || !g) return fail(g ? g->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    if (!same_shape(g, p)) return fail(g->ctx, GFB_ERR_ARG, "P and U must have the same lattice");
+    if (!std::isfinite(eps)) return fail(g->ctx, GFB_ERR_ARG, "the momentum step size must be finite");
+    GFB_CHECK(ensure_halo(g));
+    FusedArgs fa;
+    fa.a = eps * (-beta / 6.0);
+    fa.b = 1.0;
+    fa.read_z = true;
+    fa.write_z = true;
+    return fused_pass(g, g->d, nullptr, &p->d, &p->d, fa);
+}
+int gfb_update_links(gfb_gauge* g, const gfb_mom* p, double eps) {
+    if (!p || !g) return fail(g ? g->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = g->ctx;
+    if (!same_shape(g, p)) return fail(ctx, GFB_ERR_ARG, "U and P must have the same lattice");
+    if (!std::isfinite(eps)) return fail(ctx, GFB_ERR_ARG, "the gauge-field step size must be finite");
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
+        launch_update_links(ctx->slabs[i].stream, geom_of(g, i), g->d[i], g->d[i], p->d[i], eps);
+        GFB_CHECK(post_launch(ctx));
+    }
+    g->halo_valid = false;
+    return GFB_OK;
+}
+int gfb_exp_aF_U(gfb_gauge* w, double a, const gfb_mom* f, const gfb_gauge* u) {
+    if (!w || !f || !u) return fail(w ? w->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = w->ctx;
+    if (!same_shape(w, u) || !same_shape(w, f)) return fail(ctx, GFB_ERR_ARG, "fields differ in shape");
+    if (a == 0.0) return fail(ctx, GFB_ERR_ARG, "the step must not be zero in exp_aF_U");
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
+        launch_update_links(ctx->slabs[i].stream, geom_of(w, i), u->d[i], w->d[i], f->d[i], a);
+        GFB_CHECK(post_launch(ctx));
+    }
+    w->halo_valid = false;
+    return GFB_OK;
+}
+
+int gfb_md_trajectory(gfb_gauge* g, gfb_mom* p, double beta, int steps, double tau, int integrator, int fused, double* H) {
+    if (!p || !g) return fail(g ? g->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = g->ctx;
+    if (!same_shape(g, p)) return fail(ctx, GFB_ERR_ARG, "U and P must have the same lattice");
+    if (steps <= 0) return fail(ctx, GFB_ERR_ARG, "steps must be positive");
+    if (!std::isfinite(tau)) return fail(ctx, GFB_ERR_ARG, "trajectory_length must be finite");
+    if (tau == 0.0) return fail(ctx, GFB_ERR_ARG, "trajectory_length must not be zero");
+    if (integrator != GFB_QPQ && integrator != GFB_PQP) return fail(ctx, GFB_ERR_ARG, "integrator must be QPQ or PQP");
+    if (H) GFB_CHECK(gfb_hamiltonian(g, p, beta, &H[0]));
+    const double eps = tau / steps;
+    if (!fused) {
+        for (int k = 0; k < steps; k++) {
+            if (integrator == GFB_QPQ) {
+                GFB_CHECK(gfb_update_links(g, p, eps / 2));
+                GFB_CHECK(gfb_update_momenta(p, g, eps, beta));
+                GFB_CHECK(gfb_update_links(g, p, eps / 2));
+            } else {
+                GFB_CHECK(gfb_update_momenta(p, g, eps / 2, beta));
+                GFB_CHECK(gfb_update_links(g, p, eps));
+                GFB_CHECK(gfb_update_momenta(p, g, eps / 2, beta));
+            }
+        }
+    } else {
+        // leapfrog with the kick and the following drift in one kernel (double-buffered links) and the
+        // adjacent half drifts (QPQ) / half kicks (PQP) of consecutive steps merged
+        gfb_gauge_ws* ws = nullptr;
+        GFB_CHECK(get_ws(g, true, false, &ws));
+        const double kf = -beta / 6.0;
+        FusedArgs fa;
+        fa.b = 1.0; fa.read_z = true; fa.write_z = true; fa.do_exp = true;
+        if (integrator == GFB_QPQ) {
+            GFB_CHECK(gfb_update_links(g, p, eps / 2));
+            for (int k = 0; k < steps; k++) {
+                GFB_CHECK(ensure_halo(g));
+                fa.a = eps * kf;
+                fa.c = (k == steps - 1) ? eps / 2 : eps;
+                GFB_CHECK(fused_pass(g, g->d, &ws->alt, &p->d, &p->d, fa));
+                std::swap(g->d, ws->alt);
+                g->halo_valid = false;
+            }
+        } else {
+            for (int k = 0; k < steps; k++) {
+                GFB_CHECK(ensure_halo(g));
+                fa.a = ((k == 0) ? eps / 2 : eps) * kf;
+                fa.c = eps;
+                GFB_CHECK(fused_pass(g, g->d, &ws->alt, &p->d, &p->d, fa));
+                std::swap(g->d, ws->alt);
+                g->halo_valid = false;
+            }
+            GFB_CHECK(gfb_update_momenta(p, g, eps / 2, beta));
+        }
+    }
+    if (H) GFB_CHECK(gfb_hamiltonian(g, p, beta, &H[1]));
+    return GFB_OK;
+}
+
+int gfb_flow(gfb_gauge* g, double eps, int nsteps) {
+    if (!g) return fail(nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = g->ctx;
+    if (nsteps <= 0) return fail(ctx, GFB_ERR_ARG, "steps must be positive");
+    if (!(eps > 0.0) || !std::isfinite(eps)) return fail(ctx, GFB_ERR_ARG, "step_size must be positive");
+    gfb_gauge_ws* ws = nullptr;
+    GFB_CHECK(get_ws(g, true, true, &ws));
+    // Luescher RK3 in 2N-storage form (identical to gradientflow.jl:192-226 up to rounding):
+    //   Z0 = -eps F(U);             W1 = exp(Z0/4) U
+    //   Z1 = -(8/9) eps F(W1) - (17/36) Z0;  W2 = exp(Z1) W1
+    //   Z2 = -(3/4) eps F(W2) - Z1;          U' = exp(Z2) W2
+    for (int k = 0; k < nsteps; k++) {
+        FusedArgs fa;
+        fa.write_z = true; fa.do_exp = true;
+        GFB_CHECK(ensure_halo(g));
+        fa.a = -eps; fa.b = 0.0; fa.c = 0.25; fa.read_z = false;
+        GFB_CHECK(fused_pass(g, g->d, &ws->alt, nullptr, &ws->z, fa));
+        std::swap(g->d, ws->alt); g->halo_valid = false;
+        GFB_CHECK(ensure_halo(g));
+        fa.a = -(8.0 / 9.0) * eps; fa.b = -17.0 / 36.0; fa.c = 1.0; fa.read_z = true;
+        GFB_CHECK(fused_pass(g, g->d, &ws->alt, &ws->z, &ws->z, fa));
+        std::swap(g->d, ws->alt); g->halo_valid = false;
+        GFB_CHECK(ensure_halo(g));
+        fa.a = -(3.0 / 4.0) * eps; fa.b = -1.0; fa.c = 1.0; fa.read_z = true;
+        GFB_CHECK(fused_pass(g, g->d, &ws->alt, &ws->z, &ws->z, fa));
+        std::swap(g->d, ws->alt); g->halo_valid = false;
+    }
+    return GFB_OK;
+}
+
+int gfb_stout_forward(gfb_gauge* out, gfb_gauge* in, double rho, gfb_mom* q) {
+    if (!out || !in) return fail(in ? in->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = in->ctx;
+    if (out == in) return fail(ctx, GFB_ERR_ARG, "stout forward needs distinct input and output configurations");
+    if (!same_shape(out, in) || (q && !same_shape(in, q))) return fail(ctx, GFB_ERR_ARG, "fields differ in shape");
+    GFB_CHECK(ensure_halo(in));
+    // Q_mu = TA(rho * V_mu U_mu^dag) = -rho * TA(U_mu V_mu^dag);  U' = exp(Q_mu) U_mu
+    FusedArgs fa;
+    fa.a = -rho; fa.c = 1.0; fa.do_exp = true; fa.write_z = (q != nullptr);
+    GFB_CHECK(fused_pass(in, in->d, &out->d, nullptr, q ? &q->d : nullptr, fa));
+    out->halo_valid = false;
+    return GFB_OK;
+}
+
+int gfb_wilson_dSdU(gfb_gauge* d, gfb_gauge* g, double beta) {
+    if (!d || !g) return fail(g ? g->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = g->ctx;
+    if (d == g || !same_shape(d, g)) return fail(ctx, GFB_ERR_ARG, "derivative field must be a distinct configuration of the same shape");
+    GFB_CHECK(ensure_halo(g));
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
+        launch_staple_field(ctx->slabs[i].stream, geom_of(g, i), g->d[i], d->d[i], beta / 2.0);
+        GFB_CHECK(post_launch(ctx));
+    }
+    d->halo_valid = false;
+    return GFB_OK;
+}
+int gfb_kick_from_dSdU(gfb_mom* p, gfb_gauge* u, gfb_gauge* dsdu, double factor) {
+    if (!p || !u || !dsdu) return fail(u ? u->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = u->ctx;
+    if (!same_shape(u, dsdu) || !same_shape(u, p)) return fail(ctx, GFB_ERR_ARG, "fields differ in shape");
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
+        launch_kick_from_dsdu(ctx->slabs[i].stream, geom_of(u, i), u->d[i], dsdu->d[i], p->d[i], factor);
+        GFB_CHECK(post_launch(ctx));
+    }
+    return GFB_OK;
+}
+
+int gfb_stout_backward(gfb_gauge* d_in, gfb_gauge* d_out, gfb_gauge* in, double rho) {
+    (void)d_out; (void)in; (void)rho;
+    return fail(d_in ? d_in->ctx : nullptr, GFB_ERR_ARG, "gfb_stout_backward is not implemented yet");
+}
+
+}  // extern "C"

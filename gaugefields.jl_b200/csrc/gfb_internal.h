@@ -1,0 +1,110 @@
+// gfb_internal.h -- host-side structures of libgfb200 (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/gfb200.h"
+#include "lattice.cuh"
+
+namespace gfb {
+
+// One t-slab of the lattice resident on one GPU.
+struct Slab {
+    int device = 0;
+    int index = 0;  // global slab index (== NCCL rank)
+    cudaStream_t stream = nullptr;       // compute stream
+    cudaStream_t comm_stream = nullptr;  // halo stream (overlapped exchange)
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_tic = nullptr, ev_toc = nullptr;
+    ncclComm_t nccl = nullptr;
+    double* d_partial = nullptr;  // per-block partial sums
+    size_t partial_cap = 0;
+    double* d_result = nullptr;   // 8 result slots + gather area
+    double* h_result = nullptr;   // pinned mirror
+    void* d_staging = nullptr;    // AoS <-> SoA staging for upload/download
+    size_t staging_cap = 0;
+};
+
+}  // namespace gfb
+
+struct gfb_ctx {
+    std::vector<gfb::Slab> slabs;  // local slabs
+    int nslabs_total = 1;
+    bool distributed = false;  // one process per GPU
+    std::string err;
+    long long launches = 0;
+};
+
+struct gfb_gauge {
+    gfb_ctx* ctx = nullptr;
+    int nx = 0, ny = 0, nz = 0, nt = 0, tloc = 0;
+    bool has_halo = false;
+    bool halo_valid = false;
+    std::vector<double2*> d;  // per local slab
+    size_t elems_per_slab() const { return (size_t)(tloc + (has_halo ? 2 : 0)) * 36 * (size_t)nx * ny * nz; }
+    size_t slice_elems() const { return (size_t)36 * nx * ny * nz; }
+};
+
+struct gfb_mom {
+    gfb_ctx* ctx = nullptr;
+    int nx = 0, ny = 0, nz = 0, nt = 0, tloc = 0;
+    std::vector<double*> d;
+    size_t elems_per_slab() const { return (size_t)tloc * 32 * (size_t)nx * ny * nz; }
+};
+
+namespace gfb {
+
+Geom make_geom(const gfb_ctx* ctx, int nx, int ny, int nz, int nt, int slab_global_index);
+
+int fail(gfb_ctx* ctx, int code, const std::string& msg);
+
+#define GFB_CUDA(ctx, call)                                                                                   \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            return gfb::fail(ctx, GFB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+    } while (0)
+#define GFB_NCCL(ctx, call)                                                                                   \
+    do {                                                                                                      \
+        ncclResult_t r_ = (call);                                                                             \
+        if (r_ != ncclSuccess)                                                                                \
+            return gfb::fail(ctx, GFB_ERR_NCCL, std::string(#call) + ": " + ncclGetErrorString(r_));          \
+    } while (0)
+#define GFB_CHECK(expr)                    \
+    do {                                   \
+        int s_ = (expr);                   \
+        if (s_ != GFB_OK) return s_;       \
+    } while (0)
+
+// ---- kernel launch wrappers (kernels.cu); all asynchronous on the given stream ----------------
+struct FusedArgs {
+    double a = 0, b = 0, c = 0;  // Z' = a*TA(U V^dag) + b*Z ; Uout = exp(c*Z') U
+    bool read_z = false, write_z = false, do_exp = false;
+};
+void launch_force_fused(cudaStream_t st, const Geom& g, int t_begin, int t_count, const double2* uin, double2* uout, const double* zin, double* zout,
+                        const FusedArgs& fa);
+void launch_update_links(cudaStream_t st, const Geom& g, const double2* uin, double2* uout, const double* z, double c);
+void launch_plaquette(cudaStream_t st, const Geom& g, const double2* u, double* partial, int* nblocks);
+void launch_sumsq(cudaStream_t st, const double* p, size_t n, double* partial, int* nblocks);
+void launch_clover_energy(cudaStream_t st, const Geom& g, const double2* u, double* partial, int* nblocks);
+void launch_polyakov(cudaStream_t st, const Geom& g, const double2* u, double* partial, int* nblocks);  // two interleaved partial arrays
+void launch_final_reduce(cudaStream_t st, const double* partial, int n, double* out);
+int plaquette_blocks(const Geom& g);
+int sumsq_blocks(size_t n);
+void launch_links_from_host_layout(cudaStream_t st, const Geom& g, int mu, const double2* staging, double2* u);
+void launch_links_to_host_layout(cudaStream_t st, const Geom& g, int mu, const double2* u, double2* staging);
+void launch_mom_from_host_layout(cudaStream_t st, const Geom& g, int mu, const double* staging, double* p);
+void launch_mom_to_host_layout(cudaStream_t st, const Geom& g, int mu, const double* p, double* staging);
+void launch_set_cold(cudaStream_t st, const Geom& g, double2* u);
+void launch_set_hot(cudaStream_t st, const Geom& g, double2* u, unsigned long long seed);
+void launch_gaussian(cudaStream_t st, const Geom& g, double* p, unsigned long long seed, unsigned long long sweep, double sigma);
+void launch_reunitarize(cudaStream_t st, const Geom& g, double2* u);
+void launch_axpy(cudaStream_t st, double* y, double a, const double* x, size_t n);
+void launch_staple_field(cudaStream_t st, const Geom& g, const double2* u, double2* out, double scale);
+void launch_kick_from_dsdu(cudaStream_t st, const Geom& g, const double2* u, const double2* d, double* p, double factor);
+void launch_stout_lambda(cudaStream_t st, const Geom& g, const double2* u, const double2* dout, double2* lambda, double rho);
+void launch_stout_backward(cudaStream_t st, const Geom& g, const double2* u, const double2* dout, const double2* lambda, double2* din, double rho);
+
+}  // namespace gfb

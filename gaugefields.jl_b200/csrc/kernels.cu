@@ -1,0 +1,535 @@
+// kernels.cu -- hand-written sm_100a kernels of the SU(3) Wilson update path.
+//
+// All arithmetic is fp64 complex on the FP64 pipe (3x3 complex products are not a dense
+// contraction, so tensor cores do not apply); every global access is a coalesced 128-bit (links)
+// or 64-bit (momenta) access to a structure-of-arrays plane.  Roofline per kernel: DESIGN.md.
+#include <cstdio>
+
+#include "gfb_internal.h"
+#include "su3.cuh"
+
+namespace gfb {
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ M3 load_link(const double2* __restrict__ u, const Geom& g, const Coord& c, int mu) {
+    return m3_load(u + link_offset(g, c, mu), g.v3, 0);
+}
+__device__ __forceinline__ void store_link(double2* __restrict__ u, const Geom& g, const Coord& c, int mu, const M3& m) {
+    m3_store(u + link_offset(g, c, mu), g.v3, 0, m);
+}
+
+// deterministic block sum (fixed shuffle tree + fixed-order warp combine); result valid in thread 0
+__device__ __forceinline__ double block_sum(double v) {
+    __shared__ double warp_part[32];
+    const int tid = threadIdx.x + blockDim.x * threadIdx.y;
+    const int nthreads = blockDim.x * blockDim.y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((tid & 31) == 0) warp_part[tid >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (tid < 32) {
+        r = (tid < (nthreads + 31) / 32) ? warp_part[tid] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
+    }
+    __syncthreads();
+    return r;
+}
+
+// U_mu(x) * V_mu(x)^dagger with V_mu the sum of the six plaquette staples
+//   V_mu = sum_{nu != mu} [ U_nu(x) U_mu(x+nu) U_nu(x+mu)^dag + U_nu(x-nu)^dag U_mu(x-nu) U_nu(x-nu+mu) ]
+// (src/autostaples/wilsonloops.jl:468-484, construct_double_staple! src/AbstractGaugefields.jl:2856-2871)
+__device__ __forceinline__ M3 staple_sum(const double2* __restrict__ u, const Geom& g, const Coord& x, int mu) {
+    M3 s = m3_zero();
+    const Coord xm = step(g, x, mu, +1);
+#pragma unroll 1
+    for (int nu = 0; nu < 4; nu++) {
+        if (nu == mu) continue;
+        {
+            const Coord xn = step(g, x, nu, +1);
+            M3 a = load_link(u, g, x, nu);
+            M3 b = load_link(u, g, xn, mu);
+            M3 t = mul_nn(a, b);
+            a = load_link(u, g, xm, nu);
+            mac_nd(s, t, a);
+        }
+        {
+            const Coord xd = step(g, x, nu, -1);
+            const Coord xdm = step(g, xd, mu, +1);
+            M3 a = load_link(u, g, xd, nu);
+            M3 b = load_link(u, g, xd, mu);
+            M3 t = mul_dn(a, b);
+            a = load_link(u, g, xdm, nu);
+            mac_nn(s, t, a);
+        }
+    }
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused staple -> TA force -> (momentum / flow-field update) -> (exp * U)
+//   Z' = a * TAcoeffs(U_mu V_mu^dag) + b * Z ;  Uout_mu = exp(c * Z') * Uin_mu
+// One thread per (site, mu): threadIdx.x = site within the block, threadIdx.y = mu, so a warp holds
+// 32 x-consecutive sites of one direction (coalesced, no divergence in the nu loop).
+// Covers md_force!/update_momenta! (molecular_dynamics.jl:251-267,539-551), the fused leapfrog
+// step, the three RK3 flow stages (gradientflow.jl:192-226) and the stout forward layer
+// (stout_fast.jl:250-274).
+// ------------------------------------------------------------------------------------------------
+template <bool READ_Z, bool WRITE_Z, bool DO_EXP>
+__global__ void __launch_bounds__(128, 3)
+k_force_fused(Geom g, int t_begin, int t_count, const double2* __restrict__ uin, double2* __restrict__ uout, const double* __restrict__ zin,
+              double* __restrict__ zout, double a, double b, double c) {
+    const int mu = threadIdx.y;
+    const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= (long)g.v3 * t_count) return;
+    const Coord x = decode_site(g, n, t_begin, t_count);
+    M3 s = staple_sum(uin, g, x, mu);
+    const M3 umu = load_link(uin, g, x, mu);
+    double z[8];
+    {
+        M3 w = mul_nd(umu, s);
+        ta_coeffs(w, z);
+    }
+    const size_t zo = mom_offset(g, x, mu);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        double v = a * z[k];
+        if (READ_Z) v = fma(b, __ldg(zin + zo + (size_t)k * g.v3), v);
+        z[k] = v;
+        if (WRITE_Z) zout[zo + (size_t)k * g.v3] = v;
+    }
+    if (DO_EXP) {
+        M3 e = exp_ta(z, c);
+        M3 r = mul_nn(e, umu);
+        store_link(uout, g, x, mu, r);
+    }
+}
+
+void launch_force_fused(cudaStream_t st, const Geom& g, int t_begin, int t_count, const double2* uin, double2* uout, const double* zin, double* zout,
+                        const FusedArgs& fa) {
+    const int SITES = 32;
+    dim3 block(SITES, 4);
+    long nsites = (long)g.v3 * t_count;
+    dim3 grid((unsigned)((nsites + SITES - 1) / SITES));
+#define GFB_LAUNCH_FF(R, W, E) k_force_fused<R, W, E><<<grid, block, 0, st>>>(g, t_begin, t_count, uin, uout, zin, zout, fa.a, fa.b, fa.c)
+    if (fa.read_z) {
+        if (fa.do_exp) GFB_LAUNCH_FF(true, true, true);
+        else GFB_LAUNCH_FF(true, true, false);
+    } else {
+        if (fa.do_exp) {
+            if (fa.write_z) GFB_LAUNCH_FF(false, true, true);
+            else GFB_LAUNCH_FF(false, false, true);
+        } else GFB_LAUNCH_FF(false, true, false);
+    }
+#undef GFB_LAUNCH_FF
+}
+
+// ------------------------------------------------------------------------------------------------
+// link update  Uout_mu = exp(c * Z_mu) * Uin_mu  (update_gaugefields!, molecular_dynamics.jl:513-531;
+// exp_aF_U!, AbstractGaugefields.jl:2810-2841).  Site-local, so uout may alias uin.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_update_links(Geom g, const double2* uin, double2* uout, const double* __restrict__ z, double c) {
+    const int mu = blockIdx.y;
+    const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= (long)g.v3 * g.tloc) return;
+    Coord x;
+    x.t = (int)(n / g.v3);
+    int s3 = (int)(n - (long)x.t * g.v3);
+    const size_t zo = (size_t)(x.t * 32 + mu * 8) * g.v3 + s3;
+    double zz[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) zz[k] = __ldg(z + zo + (size_t)k * g.v3);
+    const size_t uo = (size_t)(x.t * 36 + mu * 9) * g.v3 + s3;
+    M3 u;
+#pragma unroll
+    for (int k = 0; k < 9; k++) u.e[k] = uin[uo + (size_t)k * g.v3];
+    M3 e = exp_ta(zz, c);
+    M3 r = mul_nn(e, u);
+#pragma unroll
+    for (int k = 0; k < 9; k++) uout[uo + (size_t)k * g.v3] = r.e[k];
+}
+void launch_update_links(cudaStream_t st, const Geom& g, const double2* uin, double2* uout, const double* z, double c) {
+    long n = (long)g.v3 * g.tloc;
+    dim3 grid((unsigned)((n + 255) / 256), 4);
+    k_update_links<<<grid, 256, 0, st>>>(g, uin, uout, z, c);
+}
+
+// ------------------------------------------------------------------------------------------------
+// reductions
+// ------------------------------------------------------------------------------------------------
+// sum_{mu<nu} Re tr P_munu(x), one thread per site (calculate_Plaquette, AbstractGaugefields.jl:2684-2699)
+__global__ void __launch_bounds__(128) k_plaquette(Geom g, const double2* __restrict__ u, double* __restrict__ partial) {
+    const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    double acc = 0.0;
+    if (n < (long)g.v3 * g.tloc) {
+        const Coord x = decode_site(g, n, 0, g.tloc);
+#pragma unroll 1
+        for (int mu = 0; mu < 3; mu++) {
+            const Coord xm = step(g, x, mu, +1);
+            const M3 umu = load_link(u, g, x, mu);
+#pragma unroll 1
+            for (int nu = mu + 1; nu < 4; nu++) {
+                const Coord xn = step(g, x, nu, +1);
+                M3 b = load_link(u, g, xm, nu);
+                M3 ab = mul_nn(umu, b);  // U_mu(x) U_nu(x+mu)
+                b = load_link(u, g, x, nu);
+                M3 c = load_link(u, g, xn, mu);
+                M3 cd = mul_nn(b, c);  // U_nu(x) U_mu(x+nu)
+                acc += retr_nd(ab, cd);
+            }
+        }
+    }
+    double r = block_sum(acc);
+    if (threadIdx.x == 0) partial[blockIdx.x] = r;
+}
+int plaquette_blocks(const Geom& g) { return (int)(((long)g.v3 * g.tloc + 127) / 128); }
+void launch_plaquette(cudaStream_t st, const Geom& g, const double2* u, double* partial, int* nblocks) {
+    int nb = plaquette_blocks(g);
+    k_plaquette<<<nb, 128, 0, st>>>(g, u, partial);
+    *nblocks = nb;
+}
+
+// sum of squares of a flat fp64 array (p*p, TA_Gaugefields.jl:127-137)
+__global__ void __launch_bounds__(256) k_sumsq(const double* __restrict__ p, size_t n, double* __restrict__ partial) {
+    double acc = 0.0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x * 2;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i + 1 < n + 1; i += stride) {
+        if (i + 1 < n) {
+            double2 v = __ldg(reinterpret_cast<const double2*>(p + i));
+            acc = fma(v.x, v.x, acc);
+            acc = fma(v.y, v.y, acc);
+        } else if (i < n) {
+            double v = p[i];
+            acc = fma(v, v, acc);
+        }
+    }
+    double r = block_sum(acc);
+    if (threadIdx.x == 0) partial[blockIdx.x] = r;
+}
+int sumsq_blocks(size_t n) {
+    size_t nb = (n / 2 + 255) / 256;
+    if (nb > 148 * 8) nb = 148 * 8;
+    if (nb < 1) nb = 1;
+    return (int)nb;
+}
+void launch_sumsq(cudaStream_t st, const double* p, size_t n, double* partial, int* nblocks) {
+    int nb = sumsq_blocks(n);
+    k_sumsq<<<nb, 256, 0, st>>>(p, n, partial);
+    *nblocks = nb;
+}
+
+// fixed-order final sum of the per-block partials (one block): deterministic for a given launch shape
+__global__ void __launch_bounds__(1024) k_final_reduce(const double* __restrict__ partial, int n, double* __restrict__ out) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partial[i];
+    double r = block_sum(acc);
+    if (threadIdx.x == 0) *out = r;
+}
+void launch_final_reduce(cudaStream_t st, const double* partial, int n, double* out) { k_final_reduce<<<1, 1024, 0, st>>>(partial, n, out); }
+
+// clover energy density numerator: sum_x sum_{mu<nu} sum_a c_a(G_munu)^2 / 2 with G = TA(4 leaves)
+// (samples/measurements/energydensity.jl:4-78; -tr(G G)/2 summed over mu != nu equals sum_{mu<nu} sum_a c_a^2/2 * 2 / 2)
+__global__ void __launch_bounds__(128) k_clover_energy(Geom g, const double2* __restrict__ u, double* __restrict__ partial) {
+    const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    double acc = 0.0;
+    if (n < (long)g.v3 * g.tloc) {
+        const Coord x = decode_site(g, n, 0, g.tloc);
+#pragma unroll 1
+        for (int mu = 0; mu < 3; mu++) {
+#pragma unroll 1
+            for (int nu = mu + 1; nu < 4; nu++) {
+                const Coord xpm = step(g, x, mu, +1), xpn = step(g, x, nu, +1);
+                const Coord xmm = step(g, x, mu, -1), xmn = step(g, x, nu, -1);
+                M3 w;
+                {  // leaf 1: U_mu(x) U_nu(x+mu) U_mu(x+nu)^dag U_nu(x)^dag
+                    M3 a = load_link(u, g, x, mu), b = load_link(u, g, xpm, nu);
+                    M3 ab = mul_nn(a, b);
+                    a = load_link(u, g, x, nu); b = load_link(u, g, xpn, mu);
+                    M3 cd = mul_nn(a, b);
+                    w = mul_nd(ab, cd);
+                }
+                {  // leaf 2: U_nu(x) U_mu(x-mu+nu)^dag U_nu(x-mu)^dag U_mu(x-mu)
+                    const Coord xmmpn = step(g, xmm, nu, +1);
+                    M3 a = load_link(u, g, x, nu), b = load_link(u, g, xmmpn, mu);
+                    M3 ab = mul_nd(a, b);
+                    a = load_link(u, g, xmm, nu); b = load_link(u, g, xmm, mu);
+                    M3 cd = mul_dn(a, b);
+                    mac_nn(w, ab, cd);
+                }
+                {  // leaf 3: U_nu(x-nu)^dag U_mu(x-nu) U_nu(x-nu+mu) U_mu(x)^dag
+                    const Coord xmnpm = step(g, xmn, mu, +1);
+                    M3 a = load_link(u, g, xmn, nu), b = load_link(u, g, xmn, mu);
+                    M3 ab = mul_dn(a, b);
+                    a = load_link(u, g, xmnpm, nu); b = load_link(u, g, x, mu);
+                    M3 cd = mul_nd(a, b);
+                    mac_nn(w, ab, cd);
+                }
+                {  // leaf 4: U_mu(x-mu)^dag U_nu(x-mu-nu)^dag U_mu(x-mu-nu) U_nu(x-nu)
+                    const Coord xmmmn = step(g, xmm, nu, -1);
+                    M3 a = load_link(u, g, xmmmn, nu), b = load_link(u, g, xmm, mu);
+                    M3 ba = mul_nn(a, b);  // U_nu(x-mu-nu) U_mu(x-mu); leaf starts with its dagger
+                    a = load_link(u, g, xmmmn, mu); b = load_link(u, g, xmn, nu);
+                    M3 cd = mul_nn(a, b);
+                    mac_dn(w, ba, cd);
+                }
+                double c[8];
+                ta_coeffs(w, c);
+#pragma unroll
+                for (int k = 0; k < 8; k++) acc = fma(0.5 * c[k], c[k], acc);
+            }
+        }
+    }
+    double r = block_sum(acc);
+    if (threadIdx.x == 0) partial[blockIdx.x] = r;
+}
+void launch_clover_energy(cudaStream_t st, const Geom& g, const double2* u, double* partial, int* nblocks) {
+    int nb = plaquette_blocks(g);
+    k_clover_energy<<<nb, 128, 0, st>>>(g, u, partial);
+    *nblocks = nb;
+}
+
+// Polyakov loop, single slab: one thread per spatial site multiplies U_t along t
+// (calculate_Polyakov_loop, AbstractGaugefields.jl:2929-2956).  partial[b] = Re, partial[gridDim+b] = Im
+__global__ void __launch_bounds__(128) k_polyakov(Geom g, const double2* __restrict__ u, double* __restrict__ partial) {
+    const int s3 = blockIdx.x * blockDim.x + threadIdx.x;
+    double re = 0.0, im = 0.0;
+    if (s3 < g.v3) {
+        M3 p = m3_load(u + (size_t)(0 * 36 + 27) * g.v3 + s3, g.v3, 0);
+        for (int t = 1; t < g.tloc; t++) {
+            M3 q = m3_load(u + (size_t)(t * 36 + 27) * g.v3 + s3, g.v3, 0);
+            p = mul_nn(p, q);
+        }
+        re = p.e[0].x + p.e[4].x + p.e[8].x;
+        im = p.e[0].y + p.e[4].y + p.e[8].y;
+    }
+    double r = block_sum(re);
+    double i = block_sum(im);
+    if (threadIdx.x == 0) { partial[blockIdx.x] = r; partial[gridDim.x + blockIdx.x] = i; }
+}
+void launch_polyakov(cudaStream_t st, const Geom& g, const double2* u, double* partial, int* nblocks) {
+    int nb = (g.v3 + 127) / 128;
+    k_polyakov<<<nb, 128, 0, st>>>(g, u, partial);
+    *nblocks = nb;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host layout <-> device layout.  staging holds this slab's chunk of the reference's gathered array
+// ComplexF64[3,3,NX,NY,NZ,T] (element (i,j) of a site at i + 3j; src/API.jl:516-529)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_links_from_host(Geom g, int mu, const double2* __restrict__ staging, double2* __restrict__ u) {
+    const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= (long)g.v3 * g.tloc) return;
+    const int t = (int)(n / g.v3);
+    const int s3 = (int)(n - (long)t * g.v3);
+    const double2* src = staging + (size_t)n * 9;
+    double2* dst = u + (size_t)(t * 36 + mu * 9) * g.v3 + s3;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) dst[(size_t)(3 * i + j) * g.v3] = src[i + 3 * j];
+}
+__global__ void __launch_bounds__(256) k_links_to_host(Geom g, int mu, const double2* __restrict__ u, double2* __restrict__ staging) {
+    const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= (long)g.v3 * g.tloc) return;
+    const int t = (int)(n / g.v3);
+    const int s3 = (int)(n - (long)t * g.v3);
+    double2* dst = staging + (size_t)n * 9;
+    const double2* src = u + (size_t)(t * 36 + mu * 9) * g.v3 + s3;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) dst[i + 3 * j] = src[(size_t)(3 * i + j) * g.v3];
+}
+__global__ void __launch_bounds__(256) k_mom_from_host(Geom g, int mu, const double* __restrict__ staging, double* __restrict__ p) {
+    const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= (long)g.v3 * g.tloc) return;
+    const int t = (int)(n / g.v3);
+    const int s3 = (int)(n - (long)t * g.v3);
+    const double2* src = reinterpret_cast<const double2*>(staging + (size_t)n * 8);
+    double* dst = p + (size_t)(t * 32 + mu * 8) * g.v3 + s3;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        double2 v = src[k];
+        dst[(size_t)(2 * k) * g.v3] = v.x;
+        dst[(size_t)(2 * k + 1) * g.v3] = v.y;
+    }
+}
+__global__ void __launch_bounds__(256) k_mom_to_host(Geom g, int mu, const double* __restrict__ p, double* __restrict__ staging) {
+    const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= (long)g.v3 * g.tloc) return;
+    const int t = (int)(n / g.v3);
+    const int s3 = (int)(n - (long)t * g.v3);
+    double2* dst = reinterpret_cast<double2*>(staging + (size_t)n * 8);
+    const double* src = p + (size_t)(t * 32 + mu * 8) * g.v3 + s3;
+#pragma unroll
+    for (int k = 0; k < 4; k++) dst[k] = make_double2(src[(size_t)(2 * k) * g.v3], src[(size_t)(2 * k + 1) * g.v3]);
+}
+static inline unsigned site_grid(const Geom& g, int bs) { return (unsigned)(((long)g.v3 * g.tloc + bs - 1) / bs); }
+void launch_links_from_host_layout(cudaStream_t st, const Geom& g, int mu, const double2* staging, double2* u) {
+    k_links_from_host<<<site_grid(g, 256), 256, 0, st>>>(g, mu, staging, u);
+}
+void launch_links_to_host_layout(cudaStream_t st, const Geom& g, int mu, const double2* u, double2* staging) {
+    k_links_to_host<<<site_grid(g, 256), 256, 0, st>>>(g, mu, u, staging);
+}
+void launch_mom_from_host_layout(cudaStream_t st, const Geom& g, int mu, const double* staging, double* p) {
+    k_mom_from_host<<<site_grid(g, 256), 256, 0, st>>>(g, mu, staging, p);
+}
+void launch_mom_to_host_layout(cudaStream_t st, const Geom& g, int mu, const double* p, double* staging) {
+    k_mom_to_host<<<site_grid(g, 256), 256, 0, st>>>(g, mu, p, staging);
+}
+
+// ------------------------------------------------------------------------------------------------
+// initial fields, RNG
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_set_cold(Geom g, double2* __restrict__ u) {
+    const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= (long)g.v3 * g.tloc) return;
+    const int mu = blockIdx.y;
+    const int t = (int)(n / g.v3);
+    const int s3 = (int)(n - (long)t * g.v3);
+    double2* dst = u + (size_t)(t * 36 + mu * 9) * g.v3 + s3;
+#pragma unroll
+    for (int k = 0; k < 9; k++) dst[(size_t)k * g.v3] = make_double2((k == 0 || k == 4 || k == 8) ? 1.0 : 0.0, 0.0);
+}
+void launch_set_cold(cudaStream_t st, const Geom& g, double2* u) { k_set_cold<<<dim3(site_grid(g, 256), 4), 256, 0, st>>>(g, u); }
+
+// stream key = first two words of Philox((seed, sweep), (tag, direction)); DESIGN.md "Random streams"
+static void host_stream_key(unsigned long long seed, unsigned long long sweep, unsigned direction, unsigned tag, unsigned* k0, unsigned* k1) {
+    unsigned o[4];
+    philox4x32_10((unsigned)seed, (unsigned)(seed >> 32), (unsigned)sweep, (unsigned)(sweep >> 32), tag, direction, o);
+    *k0 = o[0];
+    *k1 = o[1];
+}
+struct Keys4 {
+    unsigned k0[4], k1[4];
+};
+
+// hot start: 9 complex entries uniform in (-1/2,1/2)^2, filled column by column, then reunitarised
+// (randomGaugefields: gaugefields_4D_nowing.jl:240-279; keyed per global site as gaugefields_4D_MPILattice.jl:430-472)
+__global__ void __launch_bounds__(128) k_set_hot(Geom g, double2* __restrict__ u, Keys4 keys) {
+    const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= (long)g.v3 * g.tloc) return;
+    const int mu = blockIdx.y;
+    Coord x;
+    x.t = (int)(n / g.v3);
+    int s3 = (int)(n - (long)x.t * g.v3);
+    const unsigned long long gs = (unsigned long long)s3 + (unsigned long long)g.v3 * (unsigned long long)(g.t0 + x.t);
+    M3 m;
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+        double u0, u1;
+        site_uniform_pair(keys.k0[mu], keys.k1[mu], gs, (unsigned)k, u0, u1);
+        m.e[3 * (k % 3) + (k / 3)] = make_double2(u0 - 0.5, u1 - 0.5);
+    }
+    m = reunitarize(m);
+    double2* dst = u + (size_t)(x.t * 36 + mu * 9) * g.v3 + s3;
+#pragma unroll
+    for (int k = 0; k < 9; k++) dst[(size_t)k * g.v3] = m.e[k];
+}
+void launch_set_hot(cudaStream_t st, const Geom& g, double2* u, unsigned long long seed) {
+    Keys4 keys;
+    for (int mu = 0; mu < 4; mu++) host_stream_key(seed, 0ull, (unsigned)(mu + 1), 0x00484f54u, &keys.k0[mu], &keys.k1[mu]);
+    k_set_hot<<<dim3(site_grid(g, 128), 4), 128, 0, st>>>(g, u, keys);
+}
+
+// Gaussian momenta: 4 Box-Muller (value, spare) pairs per (site, direction)
+// (gauss_distribution!, TA_gaugefields_4D_MPILattice.jl:157-193; stream structure
+//  test/MPIJACCtest/random_fields_site_rng.jl:22-42)
+__global__ void __launch_bounds__(256) k_gaussian(Geom g, double* __restrict__ p, Keys4 keys, double sigma) {
+    const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= (long)g.v3 * g.tloc) return;
+    const int mu = blockIdx.y;
+    const int t = (int)(n / g.v3);
+    const int s3 = (int)(n - (long)t * g.v3);
+    const unsigned long long gs = (unsigned long long)s3 + (unsigned long long)g.v3 * (unsigned long long)(g.t0 + t);
+    double* dst = p + (size_t)(t * 32 + mu * 8) * g.v3 + s3;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        double u0, u1;
+        site_uniform_pair(keys.k0[mu], keys.k1[mu], gs, (unsigned)k, u0, u1);
+        double r = sigma * sqrt(-2.0 * log(1.0 - u0));
+        double sn, cs;
+        sincos(6.283185307179586476925286766559 * u1, &sn, &cs);
+        dst[(size_t)(2 * k) * g.v3] = r * cs;
+        dst[(size_t)(2 * k + 1) * g.v3] = r * sn;
+    }
+}
+void launch_gaussian(cudaStream_t st, const Geom& g, double* p, unsigned long long seed, unsigned long long sweep, double sigma) {
+    Keys4 keys;
+    for (int mu = 0; mu < 4; mu++) host_stream_key(seed, sweep, (unsigned)(mu + 1), 0x47415553u, &keys.k0[mu], &keys.k1[mu]);
+    k_gaussian<<<dim3(site_grid(g, 256), 4), 256, 0, st>>>(g, p, keys, sigma);
+}
+
+__global__ void __launch_bounds__(256) k_reunitarize(Geom g, double2* __restrict__ u) {
+    const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= (long)g.v3 * g.tloc) return;
+    const int mu = blockIdx.y;
+    const int t = (int)(n / g.v3);
+    const int s3 = (int)(n - (long)t * g.v3);
+    double2* p = u + (size_t)(t * 36 + mu * 9) * g.v3 + s3;
+    M3 m;
+#pragma unroll
+    for (int k = 0; k < 9; k++) m.e[k] = p[(size_t)k * g.v3];
+    m = reunitarize(m);
+#pragma unroll
+    for (int k = 0; k < 9; k++) p[(size_t)k * g.v3] = m.e[k];
+}
+void launch_reunitarize(cudaStream_t st, const Geom& g, double2* u) { k_reunitarize<<<dim3(site_grid(g, 256), 4), 256, 0, st>>>(g, u); }
+
+__global__ void __launch_bounds__(256) k_axpy(double* __restrict__ y, double a, const double* __restrict__ x, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = fma(a, x[i], y[i]);
+}
+void launch_axpy(cudaStream_t st, double* y, double a, const double* x, size_t n) {
+    size_t nb = (n + 255) / 256;
+    if (nb > 148 * 16) nb = 148 * 16;
+    k_axpy<<<(unsigned)nb, 256, 0, st>>>(y, a, x, n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// derivative-field helpers for the generic (non-fused) force path
+// ------------------------------------------------------------------------------------------------
+// out_mu(x) = scale * sum of the six staples A with tr(loop) = tr(U_mu A), i.e. scale * V_mu(x)^dagger
+// (calc_dSdUmu!, GaugeActions.jl:95-123 for the plaquette+plaquette' action with scale = beta/2)
+__global__ void __launch_bounds__(128, 3) k_staple_field(Geom g, const double2* __restrict__ u, double2* __restrict__ out, double scale) {
+    const int mu = threadIdx.y;
+    const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= (long)g.v3 * g.tloc) return;
+    const Coord x = decode_site(g, n, 0, g.tloc);
+    M3 s = staple_sum(u, g, x, mu);
+    M3 d = m3_dagger(s);
+#pragma unroll
+    for (int k = 0; k < 9; k++) { d.e[k].x *= scale; d.e[k].y *= scale; }
+    store_link(out, g, x, mu, d);
+}
+void launch_staple_field(cudaStream_t st, const Geom& g, const double2* u, double2* out, double scale) {
+    dim3 block(32, 4);
+    long nsites = (long)g.v3 * g.tloc;
+    k_staple_field<<<(unsigned)((nsites + 31) / 32), block, 0, st>>>(g, u, out, scale);
+}
+
+// P_mu += factor * TAcoeffs(U_mu * D_mu)  (md_force! tail, molecular_dynamics.jl:255-265)
+__global__ void __launch_bounds__(256) k_kick_from_dsdu(Geom g, const double2* __restrict__ u, const double2* __restrict__ d, double* __restrict__ p,
+                                                        double factor) {
+    const int mu = blockIdx.y;
+    const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= (long)g.v3 * g.tloc) return;
+    const int t = (int)(n / g.v3);
+    const int s3 = (int)(n - (long)t * g.v3);
+    const size_t uo = (size_t)(t * 36 + mu * 9) * g.v3 + s3;
+    M3 a = m3_load(u + uo, g.v3, 0), b = m3_load(d + uo, g.v3, 0);
+    M3 w = mul_nn(a, b);
+    double c[8];
+    ta_coeffs(w, c);
+    double* dst = p + (size_t)(t * 32 + mu * 8) * g.v3 + s3;
+#pragma unroll
+    for (int k = 0; k < 8; k++) dst[(size_t)k * g.v3] = fma(factor, c[k], dst[(size_t)k * g.v3]);
+}
+void launch_kick_from_dsdu(cudaStream_t st, const Geom& g, const double2* u, const double2* d, double* p, double factor) {
+    k_kick_from_dsdu<<<dim3(site_grid(g, 256), 4), 256, 0, st>>>(g, u, d, p, factor);
+}
+
+}  // namespace gfb

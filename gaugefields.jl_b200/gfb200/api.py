@@ -1,0 +1,615 @@
+"""Host-side mirror of the Gaugefields.jl high-level API for the B200 backend.
+
+Julia is not available in the build image, so this module plays the role of the Julia glue
+(`gaugefields.jl_b200/julia/B200Backend.jl`): the same entry points, argument meaning and error
+behaviour as the reference (`src/API.jl`, `src/molecular_dynamics.jl`,
+`src/smearing/gradientflow.jl`, `src/smearing/stout_fast.jl`), bound to libgfb200.so through
+ctypes exactly where Julia would `ccall`.  Julia's mutating `name!` is spelled `name_` here.
+
+Host arrays use the reference's gathered layout (src/API.jl:516-529):
+    links   : numpy complex128, shape (4, NT, NZ, NY, NX, 3, 3), last two axes (column, row)
+              == one Julia `ComplexF64[3,3,NX,NY,NZ,NT]` per direction
+    momenta : numpy float64,   shape (4, NT, NZ, NY, NX, 8) == `Float64[8,1,NX,NY,NZ,NT]`
+"""
+import ctypes
+import math
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import GfbError, check
+
+__all__ = [
+    "B200Backend", "GaugeConfiguration", "Momenta", "GaugeAction", "MDDriver", "QPQ", "PQP", "Gradientflow",
+    "StoutSmearing", "gauge_configuration", "gauge_momenta", "gaussian_momenta", "gaussian_momenta_",
+    "copy_configuration", "copy_configuration_", "measure_plaquette", "calculate_Plaquette",
+    "measure_polyakov_loop", "make_loops_fromname", "md_driver", "md_trajectory_", "md_hamiltonian",
+    "md_step_", "update_gaugefields_", "update_momenta_", "md_force_", "gradient_flow", "flow_",
+    "energy_density", "stout_smearing", "smear", "Philox4x32", "GfbError", "gauge_lattice_size",
+    "gauge_num_colors", "gauge_process_grid", "download_configuration", "upload_configuration_",
+]
+
+
+class Philox4x32:
+    """SiteRNGAlgorithm default (src/API.jl:189)."""
+    code = 0
+
+
+class QPQ:
+    """md_step! ordering Q(e/2) P(e) Q(e/2) (src/molecular_dynamics.jl:611-616)."""
+    code = 0
+
+
+class PQP:
+    """md_step! ordering P(e/2) Q(e) P(e/2) (src/molecular_dynamics.jl:604-609)."""
+    code = 1
+
+
+class B200Backend:
+    """Backend selector, the analogue of LatticeMatricesBackend() (src/API.jl:12-27).
+
+    One instance owns one libgfb200 context.  `ngpu` local GPUs are driven from this process; when
+    torch.distributed is initialised with world_size > 1 (one process per GPU, as bench.py is
+    launched by torchrun) the ranks form one context over NCCL and each rank owns one t-slab.
+    """
+
+    _default = None
+
+    def __init__(self, ngpu=1, devices=None, distributed=None):
+        lib = _lib.load()
+        self._ctx = ctypes.c_void_p()
+        self.rank, self.world = 0, 1
+        if distributed is None:
+            distributed = _dist_world() > 1
+        if distributed:
+            import torch
+            import torch.distributed as dist
+
+            self.rank, self.world = dist.get_rank(), dist.get_world_size()
+            uid = ctypes.create_string_buffer(128)
+            if self.rank == 0:
+                check(lib.gfb_nccl_unique_id(uid))
+            # share the NCCL id through the existing process group (gloo or nccl), like the reference's
+            # rank-0 seed broadcast (src/AbstractGaugefields.jl:135-150)
+            t = torch.tensor(list(uid.raw), dtype=torch.uint8)
+            if dist.get_backend() == "nccl":
+                t = t.cuda()
+            dist.broadcast(t, src=0)
+            uid = ctypes.create_string_buffer(bytes(t.cpu().tolist()), 128)
+            device = int(os.environ.get("LOCAL_RANK", self.rank)) if devices is None else int(devices[0])
+            check(lib.gfb_init_rank(self.rank, self.world, uid, device, ctypes.byref(self._ctx)))
+        else:
+            dev = None
+            if devices is not None:
+                dev = (ctypes.c_int * int(ngpu))(*[int(d) for d in devices])
+            check(lib.gfb_init(int(ngpu), dev, ctypes.byref(self._ctx)))
+        local, total = ctypes.c_int(), ctypes.c_int()
+        check(lib.gfb_num_slabs(self._ctx, ctypes.byref(local), ctypes.byref(total)), self._ctx)
+        self.local_slabs, self.total_slabs = local.value, total.value
+
+    @classmethod
+    def default(cls):
+        if cls._default is None:
+            cls._default = cls()
+        return cls._default
+
+    # -- plumbing -------------------------------------------------------------------------------
+    @property
+    def lib(self):
+        return _lib.load()
+
+    def call(self, name, *args):
+        check(getattr(self.lib, name)(*args), self._ctx)
+
+    def sync(self):
+        self.call("gfb_sync", self._ctx)
+
+    def tic(self):
+        self.call("gfb_timer_tic", self._ctx)
+
+    def toc(self):
+        ms = ctypes.c_double()
+        self.call("gfb_timer_toc", self._ctx, ctypes.byref(ms))
+        return ms.value
+
+    def kernel_launches(self):
+        n = ctypes.c_longlong()
+        self.call("gfb_kernel_launches", self._ctx, ctypes.byref(n))
+        return n.value
+
+    def t_range(self, nt):
+        """Global t-range owned by this process (all of it unless one-process-per-GPU)."""
+        if self.world == 1:
+            return 0, nt
+        tloc = nt // self.world
+        return self.rank * tloc, (self.rank + 1) * tloc
+
+    def finalize(self):
+        if self._ctx:
+            self.lib.gfb_finalize(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+
+def _dist_world():
+    try:
+        import torch.distributed as dist
+    except Exception:
+        return 1
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size()
+    return 1
+
+
+def pinned_empty(shape, dtype):
+    """numpy array over cudaMallocHost memory (fast upload/download)."""
+    lib = _lib.load()
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = ctypes.c_void_p()
+    check(lib.gfb_host_alloc(ctypes.byref(ptr), n))
+    buf = (ctypes.c_char * n).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    return arr
+
+
+# ------------------------------------------------------------------------------------------------
+# field types
+# ------------------------------------------------------------------------------------------------
+class _LinkView:
+    """U[mu]: one direction of a configuration (a Gaugefields_4D in the reference)."""
+
+    def __init__(self, parent, mu):
+        self.parent, self.mu = parent, mu
+        self.NC, self.NDW = 3, 1
+        self.NX, self.NY, self.NZ, self.NT = parent.lattice
+        self.NV = parent.NV
+
+    def to_host(self):
+        return self.parent.to_host()[self.mu]
+
+
+class GaugeConfiguration:
+    """The `Vector` of four link fields returned by gauge_configuration (src/API.jl:178-251)."""
+
+    def __init__(self, backend, lattice):
+        lattice = tuple(int(v) for v in lattice)
+        if len(lattice) != 4:
+            raise ValueError("the B200 backend supports 4 dimensions; got %d" % len(lattice))
+        if not all(v > 0 for v in lattice):
+            raise ValueError("all lattice extents must be positive; got %s" % (lattice,))
+        self.backend, self.lattice = backend, lattice
+        self.NC, self.NDW = 3, 1
+        self.NV = int(np.prod(lattice))
+        self._h = ctypes.c_void_p()
+        nx, ny, nz, nt = lattice
+        backend.call("gfb_gauge_alloc", backend._ctx, nx, ny, nz, nt, ctypes.byref(self._h))
+
+    def __len__(self):
+        return 4
+
+    def __getitem__(self, mu):
+        if not 0 <= mu < 4:
+            raise IndexError(mu)
+        return _LinkView(self, mu)
+
+    def __del__(self):
+        try:
+            if self._h and self.backend._ctx:
+                self.backend.lib.gfb_gauge_free(self._h)
+        except Exception:
+            pass
+
+    def host_shape(self):
+        nx, ny, nz, nt = self.lattice
+        return (4, nt, nz, ny, nx, 3, 3)
+
+    def upload(self, host):
+        """Load a (4,NT,NZ,NY,NX,3,3) complex128 array (gathered layout).  Each process copies its own t-range."""
+        host = np.ascontiguousarray(host, dtype=np.complex128)
+        if host.shape != self.host_shape():
+            raise ValueError("expected shape %s, got %s" % (self.host_shape(), host.shape))
+        for mu in range(4):
+            self.backend.call("gfb_gauge_upload", self._h, mu, host[mu].ctypes.data_as(ctypes.c_void_p))
+        self.backend.sync()
+        return self
+
+    def to_host(self, out=None):
+        """Gathered host copy (gather_matrix, src/API.jl:533).  One-process-per-GPU: only this rank's t-range is filled."""
+        if out is None:
+            out = np.zeros(self.host_shape(), dtype=np.complex128)
+        for mu in range(4):
+            self.backend.call("gfb_gauge_download", self._h, mu, out[mu].ctypes.data_as(ctypes.c_void_p))
+        return out
+
+
+class Momenta:
+    """Conjugate momenta: four 8-coefficient fields (initialize_TA_Gaugefields, src/TA_Gaugefields.jl:140-195)."""
+
+    def __init__(self, backend, lattice):
+        self.backend, self.lattice = backend, tuple(int(v) for v in lattice)
+        self._h = ctypes.c_void_p()
+        nx, ny, nz, nt = self.lattice
+        backend.call("gfb_mom_alloc", backend._ctx, nx, ny, nz, nt, ctypes.byref(self._h))
+
+    def __len__(self):
+        return 4
+
+    def __del__(self):
+        try:
+            if self._h and self.backend._ctx:
+                self.backend.lib.gfb_mom_free(self._h)
+        except Exception:
+            pass
+
+    def host_shape(self):
+        nx, ny, nz, nt = self.lattice
+        return (4, nt, nz, ny, nx, 8)
+
+    def upload(self, host):
+        host = np.ascontiguousarray(host, dtype=np.float64)
+        if host.shape != self.host_shape():
+            raise ValueError("expected shape %s, got %s" % (self.host_shape(), host.shape))
+        for mu in range(4):
+            self.backend.call("gfb_mom_upload", self._h, mu, host[mu].ctypes.data_as(ctypes.c_void_p))
+        self.backend.sync()
+        return self
+
+    def to_host(self, out=None):
+        if out is None:
+            out = np.zeros(self.host_shape(), dtype=np.float64)
+        for mu in range(4):
+            self.backend.call("gfb_mom_download", self._h, mu, out[mu].ctypes.data_as(ctypes.c_void_p))
+        return out
+
+    def dot(self, other=None):
+        """p * p (src/TA_Gaugefields.jl:127-137)."""
+        if other is not None and other is not self:
+            raise NotImplementedError("only p*p is provided")
+        v = ctypes.c_double()
+        self.backend.call("gfb_kinetic", self._h, ctypes.byref(v))
+        return v.value
+
+    def __mul__(self, other):
+        return self.dot(other)
+
+    def clear_(self):
+        self.backend.call("gfb_mom_zero", self._h)
+        return self
+
+    def add_(self, t, other):
+        """add_U!(P, t, F) (TA_gaugefields_4D_serial.jl:150-173)."""
+        self.backend.call("gfb_mom_axpy", self._h, float(t), other._h)
+        return self
+
+
+# ------------------------------------------------------------------------------------------------
+# configuration API (src/API.jl)
+# ------------------------------------------------------------------------------------------------
+def gauge_configuration(lattice, backend=None, colors=3, halo=1, start="cold", seed=None, process_grid=None,
+                        boundary="periodic", eltype=np.complex128, rng=Philox4x32, verbose=0):
+    """gauge_configuration(lattice; kwargs...) (src/API.jl:178-251) on the B200 backend."""
+    lattice = tuple(lattice)
+    if len(lattice) != 4:
+        raise ValueError("the B200 backend supports 4 dimensions; got %d" % len(lattice))
+    if colors != 3:
+        raise ValueError("the B200 backend supports colors=3; got %s" % colors)
+    start = str(start).lstrip(":")
+    if start not in ("cold", "hot"):
+        raise ValueError("start must be :cold or :hot; got %s" % start)
+    if int(halo) < 0:
+        raise ValueError("halo must be nonnegative; got %s" % halo)
+    if boundary != "periodic":
+        raise ValueError("the B200 backend supports periodic boundaries only")
+    if np.dtype(eltype) != np.complex128:
+        raise ValueError("the B200 backend computes in ComplexF64")
+    backend = backend or B200Backend.default()
+    U = GaugeConfiguration(backend, lattice)
+    if start == "cold":
+        backend.call("gfb_set_cold", U._h)
+    else:
+        if seed is None:
+            seed = int.from_bytes(os.urandom(8), "little") if backend.world == 1 else 0
+        backend.call("gfb_set_hot", U._h, int(seed) & (2**64 - 1), rng.code)
+    return U
+
+
+def gauge_lattice_size(U):
+    return U.lattice
+
+
+def gauge_num_colors(U):
+    return 3
+
+
+def gauge_process_grid(U):
+    """From Julia's point of view the field is undecomposed; the t-slabs are internal."""
+    return (1, 1, 1, U.backend.total_slabs)
+
+
+def copy_configuration_(destination, source):
+    """copy_configuration!(destination, source) (src/API.jl:307-322)."""
+    if destination.lattice != source.lattice:
+        raise ValueError("destination and source lattice sizes differ")
+    destination.backend.call("gfb_gauge_copy", destination._h, source._h)
+    return destination
+
+
+def copy_configuration(source):
+    dst = GaugeConfiguration(source.backend, source.lattice)
+    return copy_configuration_(dst, source)
+
+
+def upload_configuration_(U, host):
+    return U.upload(host)
+
+
+def download_configuration(U):
+    return U.to_host()
+
+
+def gauge_momenta(U):
+    """gauge_momenta(U) = initialize_TA_Gaugefields(U) (src/API.jl:331)."""
+    return Momenta(U.backend, U.lattice)
+
+
+def gaussian_momenta_(momenta, sigma=1.0, seed=None, sweep=0, rng=Philox4x32):
+    """gaussian_momenta!(momenta; sigma, seed, sweep, rng) (src/API.jl:341-368)."""
+    if sweep < 0:
+        raise ValueError("sweep must be nonnegative; got %s" % sweep)
+    if seed is None:
+        seed = int.from_bytes(os.urandom(8), "little") if momenta.backend.world == 1 else 0
+    momenta.backend.call("gfb_gaussian_momenta", momenta._h, int(seed) & (2**64 - 1), int(sweep), float(sigma), rng.code)
+    return momenta
+
+
+def gaussian_momenta(U, sigma=1.0, seed=None, sweep=0, rng=Philox4x32):
+    return gaussian_momenta_(gauge_momenta(U), sigma=sigma, seed=seed, sweep=sweep, rng=rng)
+
+
+def calculate_Plaquette(U, temp1=None, temp2=None):
+    """Un-normalised sum over x, mu<nu of Re tr P (src/AbstractGaugefields.jl:2684-2699)."""
+    v = ctypes.c_double()
+    U.backend.call("gfb_plaquette_sum", U._h, ctypes.byref(v))
+    return v.value
+
+
+def measure_plaquette(U, normalize=True):
+    """measure_plaquette(U; normalize=true) (src/API.jl:395-404)."""
+    value = calculate_Plaquette(U)
+    if not normalize:
+        return value
+    return value / (math.comb(4, 2) * U.NV * 3)
+
+
+def measure_polyakov_loop(U, normalize=True):
+    """measure_polyakov_loop (src/API.jl:412-417)."""
+    out = (ctypes.c_double * 2)()
+    U.backend.call("gfb_polyakov", U._h, out)
+    value = complex(out[0], out[1])
+    return value / 3 if normalize else value
+
+
+def energy_density(U, kind="clover"):
+    """E from the clover definition of samples/measurements/energydensity.jl:4-78, or 2*sum_{mu<nu} Re tr(1-P)/V."""
+    v = ctypes.c_double()
+    U.backend.call("gfb_energy_density", U._h, {"clover": 0, "plaquette": 1}[kind], ctypes.byref(v))
+    return v.value
+
+
+# ------------------------------------------------------------------------------------------------
+# actions (src/action/GaugeActions.jl)
+# ------------------------------------------------------------------------------------------------
+class _Loops:
+    def __init__(self, names):
+        self.names = list(names)  # entries: ("plaquette", dagger?)
+
+    def adjoint(self):
+        return _Loops([(n, not d) for n, d in self.names])
+
+    def __add__(self, other):
+        return _Loops(self.names + other.names)
+
+
+def make_loops_fromname(name, Dim=4):
+    """make_loops_fromname("plaquette", Dim=4) (Wilsonloop.jl; used at docs/src/hmc.md:146-150)."""
+    if Dim != 4:
+        raise ValueError("the B200 backend supports Dim=4")
+    if name != "plaquette":
+        raise NotImplementedError("only the plaquette loop set is fused on the B200 backend; got %r" % (name,))
+    return _Loops([("plaquette", False)])
+
+
+class GaugeAction:
+    """GaugeAction(U) + push!(action, coefficient, loops) (src/action/GaugeActions.jl:20-62).
+
+    Only the Wilson action (plaquette union plaquette') takes the fused kernels, with
+    beta = 2 * coefficient.
+    """
+
+    def __init__(self, U):
+        self.lattice = U.lattice
+        self.terms = []
+
+    def push(self, coefficient, loops):
+        self.terms.append((complex(coefficient), loops))
+        return self
+
+    def wilson_beta(self):
+        beta = 0.0
+        for coeff, loops in self.terms:
+            kinds = sorted(loops.names)
+            if kinds != [("plaquette", False), ("plaquette", True)]:
+                raise NotImplementedError(
+                    "the B200 backend fuses only plaquette+plaquette' actions; push!(action, beta/2, [plaq; plaq'])"
+                )
+            beta += 2.0 * coeff.real
+        if not self.terms:
+            raise ValueError("the action has no terms")
+        return beta
+
+
+def evaluate_GaugeAction(action, U):
+    """evaluate_GaugeAction (GaugeActions.jl:132-142): beta * sum_{x,mu<nu} Re tr P for the Wilson action."""
+    v = ctypes.c_double()
+    U.backend.call("gfb_wilson_action", U._h, action.wilson_beta(), ctypes.byref(v))
+    return complex(v.value, 0.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# molecular dynamics (src/molecular_dynamics.jl)
+# ------------------------------------------------------------------------------------------------
+class MDDriver:
+    """Preallocated deterministic MD driver (src/molecular_dynamics.jl:413-423)."""
+
+    def __init__(self, action, integrator, trajectory_length, steps, force, fused):
+        self.action, self.integrator = action, integrator
+        self.trajectory_length, self.steps = float(trajectory_length), int(steps)
+        self.force, self.fused = force, bool(fused)
+        self.beta = action.wilson_beta()
+
+
+def md_driver(U, action, steps=None, trajectory_length=1.0, integrator=QPQ, fused=True):
+    """md_driver(U, action; steps, trajectory_length=1.0, integrator=QPQ()) (src/molecular_dynamics.jl:440-483).
+
+    `fused=True` (default) runs each kick together with the following link update in one kernel
+    and merges adjacent half link updates; `fused=False` issues the reference's op sequence.
+    """
+    if steps is None:
+        raise TypeError("md_driver requires the keyword `steps`")
+    if steps <= 0:
+        raise ValueError("steps must be positive; got %s" % steps)
+    if not math.isfinite(trajectory_length):
+        raise ValueError("trajectory_length must be finite; got %s" % trajectory_length)
+    if trajectory_length == 0:
+        raise ValueError("trajectory_length must not be zero")
+    integ = integrator if isinstance(integrator, type) else type(integrator)
+    if integ not in (QPQ, PQP):
+        raise ValueError("md_step! is not implemented for %r" % (integrator,))
+    return MDDriver(action, integ, trajectory_length, steps, gauge_momenta(U), fused)
+
+
+def md_step_size(driver):
+    return driver.trajectory_length / driver.steps
+
+
+def md_hamiltonian(U, p, driver):
+    """md_hamiltonian (src/molecular_dynamics.jl:494-505): -(beta/3) sum Re tr P + p*p/2."""
+    v = ctypes.c_double()
+    U.backend.call("gfb_hamiltonian", U._h, p._h, driver.beta, ctypes.byref(v))
+    return v.value
+
+
+def update_gaugefields_(U, P, step_size, driver=None):
+    """update_gaugefields!(U, P, step_size, driver) (src/molecular_dynamics.jl:513-531)."""
+    if not math.isfinite(step_size):
+        raise ValueError("the gauge-field step size must be finite; got %s" % step_size)
+    U.backend.call("gfb_update_links", U._h, P._h, float(step_size))
+    return U
+
+
+def update_momenta_(P, U, step_size, driver):
+    """update_momenta!(P, U, step_size, driver) (src/molecular_dynamics.jl:539-551)."""
+    if not math.isfinite(step_size):
+        raise ValueError("the momentum step size must be finite; got %s" % step_size)
+    U.backend.call("gfb_update_momenta", P._h, U._h, float(step_size), driver.beta)
+    return P
+
+
+def md_force_(force, action, U, workspace=None):
+    """md_force!(force, action::GaugeAction, U, workspace) (src/molecular_dynamics.jl:251-267)."""
+    U.backend.call("gfb_force", force._h, U._h, action.wilson_beta())
+    return None
+
+
+def md_step_(integrator, U, P, step_size, driver):
+    """md_step! for PQP / QPQ (src/molecular_dynamics.jl:604-616)."""
+    integ = integrator if isinstance(integrator, type) else type(integrator)
+    if integ is PQP:
+        update_momenta_(P, U, step_size / 2, driver)
+        update_gaugefields_(U, P, step_size, driver)
+        update_momenta_(P, U, step_size / 2, driver)
+    elif integ is QPQ:
+        update_gaugefields_(U, P, step_size / 2, driver)
+        update_momenta_(P, U, step_size, driver)
+        update_gaugefields_(U, P, step_size / 2, driver)
+    else:
+        raise ValueError("md_step! is not implemented for %r" % (integrator,))
+    return None
+
+
+class TrajectoryResult(tuple):
+    """Named tuple (initial_hamiltonian, final_hamiltonian, delta_hamiltonian)."""
+
+    def __new__(cls, h0, h1):
+        return super().__new__(cls, (h0, h1, h1 - h0))
+
+    initial_hamiltonian = property(lambda s: s[0])
+    final_hamiltonian = property(lambda s: s[1])
+    delta_hamiltonian = property(lambda s: s[2])
+
+
+def md_trajectory_(U, P, driver, diagnostics=True):
+    """md_trajectory!(U, p, driver; diagnostics=true) (src/molecular_dynamics.jl:712-730)."""
+    if U.lattice != P.lattice:
+        raise ValueError("U and P must have the same number of directions / lattice")
+    H = (ctypes.c_double * 2)() if diagnostics else None
+    U.backend.call(
+        "gfb_md_trajectory", U._h, P._h, driver.beta, driver.steps, driver.trajectory_length, driver.integrator.code,
+        1 if driver.fused else 0, H,
+    )
+    if not diagnostics:
+        return None
+    return TrajectoryResult(H[0], H[1])
+
+
+# ------------------------------------------------------------------------------------------------
+# gradient flow (src/smearing/gradientflow.jl) and stout smearing (src/smearing/stout_fast.jl)
+# ------------------------------------------------------------------------------------------------
+class Gradientflow:
+    """Gradientflow(U; Nflow=1, eps=0.01) (src/smearing/gradientflow.jl:118-161)."""
+
+    def __init__(self, U, Nflow=1, eps=0.01):
+        self.Nflow, self.eps = int(Nflow), float(eps)
+
+
+def gradient_flow(U, steps=1, step_size=0.01):
+    """gradient_flow(U; steps, step_size) (src/API.jl:420-424)."""
+    if steps <= 0:
+        raise ValueError("steps must be positive; got %s" % steps)
+    if not step_size > 0:
+        raise ValueError("step_size must be positive; got %s" % step_size)
+    return Gradientflow(U, Nflow=steps, eps=step_size)
+
+
+def flow_(U, g):
+    """flow!(U, g::Gradientflow) (src/smearing/gradientflow.jl:171-238): g.Nflow RK3 steps."""
+    U.backend.call("gfb_flow", U._h, g.eps, g.Nflow)
+    return U
+
+
+class StoutSmearing:
+    """One or more plaquette-staple stout layers (stout_smearing, src/API.jl:452-466)."""
+
+    def __init__(self, rhos):
+        self.rhos = [float(r) for r in rhos]
+
+
+def stout_smearing(U, loops="plaquette", rho=0.1, layers=1):
+    if str(loops).lstrip(":") != "plaquette":
+        raise NotImplementedError("the B200 backend implements plaquette-staple stout smearing")
+    return StoutSmearing([rho] * int(layers))
+
+
+def smear(U, smearing, record=False):
+    """smear(U, smearing; record=false) (src/API.jl:468-480): returns the smeared configuration
+    (and, with record=True, the per-layer inputs needed by back_prop)."""
+    history = []
+    cur = U
+    for rho in smearing.rhos:
+        out = GaugeConfiguration(U.backend, U.lattice)
+        U.backend.call("gfb_stout_forward", out._h, cur._h, rho, None)
+        history.append(cur)
+        cur = out
+    if record:
+        return {"configuration": cur, "history": history}
+    return cur
