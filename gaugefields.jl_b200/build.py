@@ -12,7 +12,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = ["kernels.cu", "stout.cu", "api.cu"]
 HEADERS = ["su3.cuh", "lattice.cuh", "gfb_internal.h", os.path.join("..", "..", "include", "gfb200.h")]
-LIB = os.path.join(HERE, "libgfb200.so")
+# GFB200_VARIANT=<name> + GFB200_NVCC_EXTRA="-D..." build a tuning variant next to the default library
+VARIANT = os.environ.get("GFB200_VARIANT", "")
+LIB = os.path.join(HERE, "libgfb200%s.so" % (("_" + VARIANT) if VARIANT else ""))
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
@@ -35,13 +37,15 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    bdir = os.path.join(HERE, "build", VARIANT or "default")
+    os.makedirs(bdir, exist_ok=True)
+    extra = os.environ.get("GFB200_NVCC_EXTRA", "").split()
     for s in SOURCES:
         src = os.path.join(CSRC, s)
         if not os.path.exists(src):
             continue
-        obj = os.path.join(HERE, "build", s.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        obj = os.path.join(bdir, s.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd)))
         objs.append(obj)
     for cmd, p in procs:

@@ -54,7 +54,8 @@ static int check_dims(gfb_ctx* ctx, int nx, int ny, int nz, int nt) {
     if (nx <= 0 || ny <= 0 || nz <= 0 || nt <= 0) return fail(ctx, GFB_ERR_ARG, "all lattice extents must be positive");
     if (nt % ctx->nslabs_total != 0) return fail(ctx, GFB_ERR_ARG, "NT must be divisible by the number of GPUs (t-slab decomposition)");
     if (ctx->nslabs_total > 1 && nt / ctx->nslabs_total < 2) return fail(ctx, GFB_ERR_ARG, "each t-slab needs at least 2 time-slices");
-    if ((double)nx * ny * nz > 2.0e9 / 36.0) return fail(ctx, GFB_ERR_ARG, "spatial volume too large for 32-bit slice indexing");
+    if ((double)nx * ny * nz * 36.0 * (nt / ctx->nslabs_total + 2) >= 2147483647.0)
+        return fail(ctx, GFB_ERR_ARG, "local slab too large for 32-bit element indexing (nslots*36*NX*NY*NZ must stay below 2^31)");
     return GFB_OK;
 }
 

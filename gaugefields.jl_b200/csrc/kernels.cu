@@ -8,16 +8,26 @@
 #include "gfb_internal.h"
 #include "su3.cuh"
 
+// tuning knobs of the fused force kernel (see profiles/ and DESIGN.md)
+#ifndef GFB_FF_MINBLOCKS
+#define GFB_FF_MINBLOCKS 4
+#endif
+#ifndef GFB_FF_UNROLL
+#define GFB_FF_UNROLL 1
+#endif
+
 namespace gfb {
+
+constexpr int kStapleUnroll = GFB_FF_UNROLL;
 
 // ------------------------------------------------------------------------------------------------
 // helpers
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ M3 load_link(const double2* __restrict__ u, const Geom& g, const Coord& c, int mu) {
-    return m3_load(u + link_offset(g, c, mu), g.v3, 0);
+    return m3_load(u + link_offset(g, c, mu), (unsigned)g.v3);
 }
 __device__ __forceinline__ void store_link(double2* __restrict__ u, const Geom& g, const Coord& c, int mu, const M3& m) {
-    m3_store(u + link_offset(g, c, mu), g.v3, 0, m);
+    m3_store(u + link_offset(g, c, mu), (unsigned)g.v3, m);
 }
 
 // deterministic block sum (fixed shuffle tree + fixed-order warp combine); result valid in thread 0
@@ -45,7 +55,7 @@ __device__ __forceinline__ double block_sum(double v) {
 __device__ __forceinline__ M3 staple_sum(const double2* __restrict__ u, const Geom& g, const Coord& x, int mu) {
     M3 s = m3_zero();
     const Coord xm = step(g, x, mu, +1);
-#pragma unroll 1
+#pragma unroll kStapleUnroll
     for (int nu = 0; nu < 4; nu++) {
         if (nu == mu) continue;
         {
@@ -79,7 +89,7 @@ __device__ __forceinline__ M3 staple_sum(const double2* __restrict__ u, const Ge
 // (stout_fast.jl:250-274).
 // ------------------------------------------------------------------------------------------------
 template <bool READ_Z, bool WRITE_Z, bool DO_EXP>
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(128, GFB_FF_MINBLOCKS)
 k_force_fused(Geom g, int t_begin, int t_count, const double2* __restrict__ uin, double2* __restrict__ uout, const double* __restrict__ zin,
               double* __restrict__ zout, double a, double b, double c) {
     const int mu = threadIdx.y;
@@ -93,13 +103,14 @@ k_force_fused(Geom g, int t_begin, int t_count, const double2* __restrict__ uin,
         M3 w = mul_nd(umu, s);
         ta_coeffs(w, z);
     }
-    const size_t zo = mom_offset(g, x, mu);
+    const unsigned zo = mom_offset(g, x, mu);
+    const unsigned zsb = (unsigned)g.v3 * 8u;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         double v = a * z[k];
-        if (READ_Z) v = fma(b, __ldg(zin + zo + (size_t)k * g.v3), v);
+        if (READ_Z) v = fma(b, __ldg(reinterpret_cast<const double*>(reinterpret_cast<const char*>(zin + zo) + (size_t)k * zsb)), v);
         z[k] = v;
-        if (WRITE_Z) zout[zo + (size_t)k * g.v3] = v;
+        if (WRITE_Z) *reinterpret_cast<double*>(reinterpret_cast<char*>(zout + zo) + (size_t)k * zsb) = v;
     }
     if (DO_EXP) {
         M3 e = exp_ta(z, c);
@@ -297,9 +308,9 @@ __global__ void __launch_bounds__(128) k_polyakov(Geom g, const double2* __restr
     const int s3 = blockIdx.x * blockDim.x + threadIdx.x;
     double re = 0.0, im = 0.0;
     if (s3 < g.v3) {
-        M3 p = m3_load(u + (size_t)(0 * 36 + 27) * g.v3 + s3, g.v3, 0);
+        M3 p = m3_load(u + (size_t)(0 * 36 + 27) * g.v3 + s3, (unsigned)g.v3);
         for (int t = 1; t < g.tloc; t++) {
-            M3 q = m3_load(u + (size_t)(t * 36 + 27) * g.v3 + s3, g.v3, 0);
+            M3 q = m3_load(u + (size_t)(t * 36 + 27) * g.v3 + s3, (unsigned)g.v3);
             p = mul_nn(p, q);
         }
         re = p.e[0].x + p.e[4].x + p.e[8].x;
@@ -520,7 +531,7 @@ __global__ void __launch_bounds__(256) k_kick_from_dsdu(Geom g, const double2* _
     const int t = (int)(n / g.v3);
     const int s3 = (int)(n - (long)t * g.v3);
     const size_t uo = (size_t)(t * 36 + mu * 9) * g.v3 + s3;
-    M3 a = m3_load(u + uo, g.v3, 0), b = m3_load(d + uo, g.v3, 0);
+    M3 a = m3_load(u + uo, (unsigned)g.v3), b = m3_load(d + uo, (unsigned)g.v3);
     M3 w = mul_nn(a, b);
     double c[8];
     ta_coeffs(w, c);

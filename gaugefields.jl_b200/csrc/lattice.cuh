@@ -63,12 +63,13 @@ __device__ __forceinline__ Coord step(const Geom& g, Coord c, int dir, int sgn) 
 __device__ __forceinline__ int s3_of(const Geom& g, const Coord& c) { return c.x + g.nx * (c.y + g.ny * c.z); }
 
 // offset (in double2) of element 0 of link mu at site c; element k is k*v3 further
-__device__ __forceinline__ size_t link_offset(const Geom& g, const Coord& c, int mu) {
-    return (size_t)(c.t * 36 + mu * 9) * (size_t)g.v3 + (size_t)s3_of(g, c);
+// (32-bit: check_dims guarantees nslots*36*v3 < 2^31)
+__device__ __forceinline__ unsigned link_offset(const Geom& g, const Coord& c, int mu) {
+    return (unsigned)(c.t * 36 + mu * 9) * (unsigned)g.v3 + (unsigned)s3_of(g, c);
 }
 // offset (in double) of coefficient 0 of momentum mu at site c; coefficient a is a*v3 further
-__device__ __forceinline__ size_t mom_offset(const Geom& g, const Coord& c, int mu) {
-    return (size_t)(c.t * 32 + mu * 8) * (size_t)g.v3 + (size_t)s3_of(g, c);
+__device__ __forceinline__ unsigned mom_offset(const Geom& g, const Coord& c, int mu) {
+    return (unsigned)(c.t * 32 + mu * 8) * (unsigned)g.v3 + (unsigned)s3_of(g, c);
 }
 // global site id (x fastest, global t) used to key the per-site RNG streams
 __device__ __forceinline__ unsigned long long global_site_id(const Geom& g, const Coord& c) {

@@ -152,16 +152,31 @@ __device__ __forceinline__ void m3_add(M3& c, const M3& a) {
     for (int k = 0; k < 9; k++) { c.e[k].x += a.e[k].x; c.e[k].y += a.e[k].y; }
 }
 
-// structure-of-arrays access: element k of the matrix at `site` lives at p[k*plane + site]
-__device__ __forceinline__ M3 m3_load(const double2* __restrict__ p, long plane, long site) {
+// structure-of-arrays access: element k of the matrix lives `k*plane` elements after element 0.
+// The address of element k is formed as base + k*(plane*16) with a 32-bit byte stride, which ptxas
+// turns into ONE IMAD.WIDE.U32 per 128-bit access (64-bit index arithmetic costs 4 integer
+// instructions per load and steals issue slots from the FP64 pipe).
+__device__ __forceinline__ M3 m3_load(const double2* __restrict__ p, unsigned plane) {
     M3 r;
+    const char* b = reinterpret_cast<const char*>(p);
+    const unsigned sb = plane * 16u;
 #pragma unroll
-    for (int k = 0; k < 9; k++) r.e[k] = __ldg(p + k * plane + site);
+    for (int k = 0; k < 9; k++) r.e[k] = __ldg(reinterpret_cast<const double2*>(b + (size_t)k * sb));
     return r;
 }
-__device__ __forceinline__ void m3_store(double2* __restrict__ p, long plane, long site, const M3& m) {
+__device__ __forceinline__ M3 m3_load_rw(const double2* p, unsigned plane) {
+    M3 r;
+    const char* b = reinterpret_cast<const char*>(p);
+    const unsigned sb = plane * 16u;
 #pragma unroll
-    for (int k = 0; k < 9; k++) p[k * plane + site] = m.e[k];
+    for (int k = 0; k < 9; k++) r.e[k] = *reinterpret_cast<const double2*>(b + (size_t)k * sb);
+    return r;
+}
+__device__ __forceinline__ void m3_store(double2* __restrict__ p, unsigned plane, const M3& m) {
+    char* b = reinterpret_cast<char*>(p);
+    const unsigned sb = plane * 16u;
+#pragma unroll
+    for (int k = 0; k < 9; k++) *reinterpret_cast<double2*>(b + (size_t)k * sb) = m.e[k];
 }
 
 #define GFB_SR3I 0.57735026918962576451  // 1/sqrt(3)
@@ -379,7 +394,7 @@ __device__ __forceinline__ M3 reunitarize(const M3& m) {
     return u;
 }
 
-// Philox4x32-10 (Salmon et al., SC'11); identical to oracle/gf_oracle.cpp::philox4x32_10
+// Philox4x32-10 (Salmon et al., SC11), checked against the Random123 known-answer vectors
 __device__ __host__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned* out) {
     const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll

@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG, "libgfb200.so")
+# GFB200_LIB selects a tuning variant built by build.py (default: libgfb200.so)
+LIB_PATH = os.environ.get("GFB200_LIB") or os.path.join(_PKG, "libgfb200.so")
 
 c_int, c_double, c_void_p, c_char_p = ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_char_p
 c_u64, c_size_t, c_ll = ctypes.c_uint64, ctypes.c_size_t, ctypes.c_longlong

@@ -203,22 +203,39 @@ class GaugeConfiguration:
         nx, ny, nz, nt = self.lattice
         return (4, nt, nz, ny, nx, 3, 3)
 
-    def upload(self, host):
-        """Load a (4,NT,NZ,NY,NX,3,3) complex128 array (gathered layout).  Each process copies its own t-range."""
+    def local_shape(self):
+        nx, ny, nz, nt = self.lattice
+        t0, t1 = self.backend.t_range(nt)
+        return (4, t1 - t0, nz, ny, nx, 3, 3)
+
+    def _ptr(self, host, mu, local):
+        # the C ABI takes the GLOBAL array of one direction and touches only this context's t-range; a
+        # rank-local chunk is passed as the pointer the global array would have had
+        base = host[mu].ctypes.data
+        if local:
+            nx, ny, nz, nt = self.lattice
+            t0, _ = self.backend.t_range(nt)
+            base -= t0 * nx * ny * nz * 9 * 16
+        return ctypes.c_void_p(base)
+
+    def upload(self, host, local=False):
+        """Load a (4,NT,NZ,NY,NX,3,3) complex128 array (gathered layout); each process copies its own t-range.
+        With local=True `host` holds only this process's t-range (shape local_shape())."""
         host = np.ascontiguousarray(host, dtype=np.complex128)
-        if host.shape != self.host_shape():
-            raise ValueError("expected shape %s, got %s" % (self.host_shape(), host.shape))
+        want = self.local_shape() if local else self.host_shape()
+        if host.shape != want:
+            raise ValueError("expected shape %s, got %s" % (want, host.shape))
         for mu in range(4):
-            self.backend.call("gfb_gauge_upload", self._h, mu, host[mu].ctypes.data_as(ctypes.c_void_p))
+            self.backend.call("gfb_gauge_upload", self._h, mu, self._ptr(host, mu, local))
         self.backend.sync()
         return self
 
-    def to_host(self, out=None):
+    def to_host(self, out=None, local=False):
         """Gathered host copy (gather_matrix, src/API.jl:533).  One-process-per-GPU: only this rank's t-range is filled."""
         if out is None:
-            out = np.zeros(self.host_shape(), dtype=np.complex128)
+            out = np.zeros(self.local_shape() if local else self.host_shape(), dtype=np.complex128)
         for mu in range(4):
-            self.backend.call("gfb_gauge_download", self._h, mu, out[mu].ctypes.data_as(ctypes.c_void_p))
+            self.backend.call("gfb_gauge_download", self._h, mu, self._ptr(out, mu, local))
         return out
 
 
@@ -245,20 +262,34 @@ class Momenta:
         nx, ny, nz, nt = self.lattice
         return (4, nt, nz, ny, nx, 8)
 
-    def upload(self, host):
+    def local_shape(self):
+        nx, ny, nz, nt = self.lattice
+        t0, t1 = self.backend.t_range(nt)
+        return (4, t1 - t0, nz, ny, nx, 8)
+
+    def _ptr(self, host, mu, local):
+        base = host[mu].ctypes.data
+        if local:
+            nx, ny, nz, nt = self.lattice
+            t0, _ = self.backend.t_range(nt)
+            base -= t0 * nx * ny * nz * 8 * 8
+        return ctypes.c_void_p(base)
+
+    def upload(self, host, local=False):
         host = np.ascontiguousarray(host, dtype=np.float64)
-        if host.shape != self.host_shape():
-            raise ValueError("expected shape %s, got %s" % (self.host_shape(), host.shape))
+        want = self.local_shape() if local else self.host_shape()
+        if host.shape != want:
+            raise ValueError("expected shape %s, got %s" % (want, host.shape))
         for mu in range(4):
-            self.backend.call("gfb_mom_upload", self._h, mu, host[mu].ctypes.data_as(ctypes.c_void_p))
+            self.backend.call("gfb_mom_upload", self._h, mu, self._ptr(host, mu, local))
         self.backend.sync()
         return self
 
-    def to_host(self, out=None):
+    def to_host(self, out=None, local=False):
         if out is None:
-            out = np.zeros(self.host_shape(), dtype=np.float64)
+            out = np.zeros(self.local_shape() if local else self.host_shape(), dtype=np.float64)
         for mu in range(4):
-            self.backend.call("gfb_mom_download", self._h, mu, out[mu].ctypes.data_as(ctypes.c_void_p))
+            self.backend.call("gfb_mom_download", self._h, mu, self._ptr(out, mu, local))
         return out
 
     def dot(self, other=None):

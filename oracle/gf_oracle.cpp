@@ -153,11 +153,11 @@ inline M3 hermitian_from_coeffs(const double* u, double t) {
 inline M3 exp_taylor(const M3& x) {
     double nrm = norm1(x);
     int s = 0;
-    while (nrm > 0.125) { nrm *= 0.5; s++; }
+    while (nrm > 1.0) { nrm *= 0.5; s++; }  // few squarings: each one doubles the rounding error
     M3 y = scale(std::ldexp(1.0, -s), x);
     M3 r = ident3();
     M3 term = ident3();
-    for (int n = 1; n <= 18; n++) {
+    for (int n = 1; n <= 30; n++) {
         term = scale(1.0 / n, mul(term, y));
         r = add(r, term);
     }
@@ -551,6 +551,28 @@ void orc_flow_step(double* U, const int* dims, double eps) {
     orc_flow_force(F2.data(), W2.data(), dims);
     for (size_t i = 0; i < nf; i++) Ft[i] = -(3 * eps / 4) * F2[i] + (8 * eps / 9) * F1[i] - (17 * eps / 36) * F0[i];
     orc_update_links_route(U, W2.data(), Ft.data(), dims, 1.0, 0);
+}
+
+
+// ----------------------------------------------------------------------------- stout smearing
+
+// STOUT_Layer forward! (src/smearing/stout_fast.jl:250-274, calc_C! :603-624) for the plaquette staple with scalar rho:
+//   C_mu = rho * V_mu ;  Q_mu = TA(C_mu U_mu^dag) (matrix-valued, nowing:1253-1345) ;  U'_mu = exp(Q_mu) U_mu
+// Qout (may be NULL) receives the 8 coefficients of Q_mu.
+void orc_stout_forward(double* Uout, const double* Uin, const int* dims, double rho, double* Qout) {
+    Lat L(dims);
+#pragma omp parallel for
+    for (long s = 0; s < L.V; s++) {
+        int x[4];
+        L.coord(s, x);
+        for (int mu = 0; mu < 4; mu++) {
+            M3 u = getU(Uin, L, mu, s);
+            M3 c = scale(rho, staple_sum(Uin, L, x, mu));
+            M3 q = ta_matrix(mul(c, dag(u)));
+            if (Qout) ta_coeffs(q, Qout + ((long)mu * L.V + s) * 8);
+            setU(Uout, L, mu, s, mul(exp_taylor(q), u));
+        }
+    }
 }
 
 // ----------------------------------------------------------------------------- single-matrix probes (unit tests)

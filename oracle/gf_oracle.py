@@ -191,3 +191,10 @@ def staple_sum(U, dims):
     V = np.empty_like(U)
     lib().orc_staple_sum(_dp(V), _dp(U), _dims(dims))
     return V
+
+
+def stout_forward(U, dims, rho, want_q=False):
+    out = np.empty_like(U)
+    Q = new_p(dims) if want_q else None
+    lib().orc_stout_forward(_dp(out), _dp(U), _dims(dims), ctypes.c_double(rho), _dp(Q) if want_q else None)
+    return (out, Q) if want_q else out
