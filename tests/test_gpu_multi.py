@@ -1,0 +1,110 @@
+"""Multi-GPU parity (t-slab decomposition + NCCL halo exchange).
+
+Needs >= 2 GPUs on the box (`gpurun --gpus 2`); skipped otherwise.  Covers both launch forms:
+one process driving two GPUs (gfb_init) and one process per GPU under torchrun (gfb_init_rank)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def ngpus():
+    import torch
+
+    return torch.cuda.device_count()
+
+
+@pytest.fixture(scope="module")
+def backend2():
+    if ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    import gfb200
+
+    b = gfb200.B200Backend(ngpu=2)
+    yield b
+
+
+DIMS = (4, 6, 4, 8)
+
+
+def test_two_slabs_match_oracle(backend2, oracle):
+    import gfb200
+
+    dims = DIMS
+    Uh = oracle.hot_start_philox(dims, 1234)
+    U = gfb200.gauge_configuration(dims, backend=backend2).upload(Uh)
+    assert gfb200.gauge_process_grid(U) == (1, 1, 1, 2)
+    assert np.array_equal(U.to_host(), Uh)
+    want = oracle.plaquette_sum(Uh, dims)
+    assert abs(gfb200.calculate_Plaquette(U) - want) <= 1e-12 * abs(want) + 1e-12
+    loops = gfb200.make_loops_fromname("plaquette")
+    action = gfb200.GaugeAction(U).push(5.7 / 2, loops + loops.adjoint())
+    F = gfb200.gauge_momenta(U)
+    gfb200.md_force_(F, action, U)
+    Fw = oracle.force(Uh, dims, 5.7)
+    assert np.abs(F.to_host() - Fw).max() / np.abs(Fw).max() < 1e-12
+    e = gfb200.energy_density(U)
+    assert abs(e - oracle.energy_density_clover(Uh, dims)) < 1e-11 * max(1.0, abs(e))
+    for integ in (gfb200.QPQ, gfb200.PQP):
+        for fused in (False, True):
+            U.upload(Uh)
+            Ph = oracle.gaussian_momenta(dims, 0x5678, 1)
+            P = gfb200.gauge_momenta(U).upload(Ph)
+            md = gfb200.md_driver(U, action, steps=10, trajectory_length=0.5, integrator=integ, fused=fused)
+            res = gfb200.md_trajectory_(U, P, md)
+            Uo = Uh.copy()
+            H0, H1 = oracle.md_trajectory(Uo, Ph, dims, 5.7, 10, 0.5, integ.code)
+            assert abs(res.delta_hamiltonian - (H1 - H0)) < 1e-9
+            assert np.abs(U.to_host() - Uo).max() < 1e-11
+    U.upload(Uh)
+    gfb200.flow_(U, gfb200.gradient_flow(U, steps=3, step_size=0.01))
+    Uo = Uh.copy()
+    for _ in range(3):
+        oracle.flow_step(Uo, dims, 0.01)
+    assert np.abs(U.to_host() - Uo).max() < 1e-12
+    U.upload(Uh)
+    out = gfb200.smear(U, gfb200.stout_smearing(U, rho=0.1, layers=2))
+    want = oracle.stout_forward(oracle.stout_forward(Uh, dims, 0.1), dims, 0.1)
+    assert np.abs(out.to_host() - want).max() < 1e-12
+
+
+def test_random_fields_are_decomposition_independent(backend2, backend):
+    """hot start and Gaussian momenta are keyed by the GLOBAL site: bit-identical on 1 and 2 slabs
+    (test/MPIJACCtest/random_fields_site_rng.jl:148-172)."""
+    import gfb200
+
+    dims = DIMS
+    a = gfb200.gauge_configuration(dims, backend=backend, start="hot", seed=99).to_host()
+    b = gfb200.gauge_configuration(dims, backend=backend2, start="hot", seed=99).to_host()
+    assert np.array_equal(a, b)
+    U1 = gfb200.gauge_configuration(dims, backend=backend)
+    U2 = gfb200.gauge_configuration(dims, backend=backend2)
+    pa = gfb200.gaussian_momenta(U1, seed=5, sweep=7).to_host()
+    pb = gfb200.gaussian_momenta(U2, seed=5, sweep=7).to_host()
+    assert np.array_equal(pa, pb)
+
+
+def test_slab_constraints(backend2):
+    import gfb200
+
+    with pytest.raises(ValueError):
+        gfb200.gauge_configuration((4, 4, 4, 5), backend=backend2)  # NT not divisible by 2
+    with pytest.raises(ValueError):
+        gfb200.gauge_configuration((4, 4, 4, 2), backend=backend2)  # one slice per slab
+
+
+@pytest.mark.timeout(600)
+def test_one_process_per_gpu_under_torchrun():
+    if ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(ROOT, "scripts", "dist_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=500, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "dist_check ok" in r.stdout
