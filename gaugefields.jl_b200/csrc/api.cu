@@ -872,8 +872,27 @@ int gfb_kick_from_dSdU(gfb_mom* p, gfb_gauge* u, gfb_gauge* dsdu, double factor)
 }
 
 int gfb_stout_backward(gfb_gauge* d_in, gfb_gauge* d_out, gfb_gauge* in, double rho) {
-    (void)d_out; (void)in; (void)rho;
-    return fail(d_in ? d_in->ctx : nullptr, GFB_ERR_ARG, "gfb_stout_backward is not implemented yet");
+    if (!d_in || !d_out || !in) return fail(in ? in->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = in->ctx;
+    if (d_in == d_out || d_in == in) return fail(ctx, GFB_ERR_ARG, "stout backward needs a distinct output field");
+    if (!same_shape(d_in, in) || !same_shape(d_out, in)) return fail(ctx, GFB_ERR_ARG, "fields differ in shape");
+    if (!std::isfinite(rho)) return fail(ctx, GFB_ERR_ARG, "rho must be finite");
+    gfb_gauge_ws* ws = nullptr;
+    GFB_CHECK(get_ws(d_in, true, false, &ws));  // Lambda = dS/dC lives in d_in's spare buffer (same layout, with halo slots)
+    GFB_CHECK(ensure_halo(in));
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
+        launch_stout_lambda(ctx->slabs[i].stream, geom_of(in, i), in->d[i], d_out->d[i], ws->alt[i], d_in->d[i], rho);
+        GFB_CHECK(post_launch(ctx));
+    }
+    GFB_CHECK(exchange_halo_buffers(ctx, d_in, ws->alt, false));  // neighbours' Lambda on the slab faces
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
+        launch_stout_backward(ctx->slabs[i].stream, geom_of(in, i), in->d[i], ws->alt[i], d_in->d[i], rho);
+        GFB_CHECK(post_launch(ctx));
+    }
+    d_in->halo_valid = false;
+    return GFB_OK;
 }
 
 }  // extern "C"

@@ -104,7 +104,7 @@ void launch_reunitarize(cudaStream_t st, const Geom& g, double2* u);
 void launch_axpy(cudaStream_t st, double* y, double a, const double* x, size_t n);
 void launch_staple_field(cudaStream_t st, const Geom& g, const double2* u, double2* out, double scale);
 void launch_kick_from_dsdu(cudaStream_t st, const Geom& g, const double2* u, const double2* d, double* p, double factor);
-void launch_stout_lambda(cudaStream_t st, const Geom& g, const double2* u, const double2* dout, double2* lambda, double rho);
-void launch_stout_backward(cudaStream_t st, const Geom& g, const double2* u, const double2* dout, const double2* lambda, double2* din, double rho);
+void launch_stout_lambda(cudaStream_t st, const Geom& g, const double2* u, const double2* dout, double2* lambda, double2* din, double rho);
+void launch_stout_backward(cudaStream_t st, const Geom& g, const double2* u, const double2* lambda, double2* din, double rho);
 
 }  // namespace gfb

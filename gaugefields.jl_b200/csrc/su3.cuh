@@ -237,7 +237,7 @@ __device__ __forceinline__ M3 ta_from_coeffs(const double* c) {
     return q;
 }
 
-__constant__ double c_inv_factorial[24] = {
+static __constant__ double c_inv_factorial[24] = {
     1.0,
     1.0,
     1.0 / 2.0,

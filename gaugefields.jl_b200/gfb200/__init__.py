@@ -5,6 +5,6 @@ reference's package name does), then `import gfb200`.
 """
 from . import _lib
 from .api import *  # noqa: F401,F403
-from .api import evaluate_GaugeAction, md_step_size, pinned_empty  # noqa: F401
+from .api import md_step_size, pinned_empty  # noqa: F401
 
 LIB_PATH = _lib.LIB_PATH

@@ -28,6 +28,7 @@ __all__ = [
     "md_step_", "update_gaugefields_", "update_momenta_", "md_force_", "gradient_flow", "flow_",
     "energy_density", "stout_smearing", "smear", "Philox4x32", "GfbError", "gauge_lattice_size",
     "gauge_num_colors", "gauge_process_grid", "download_configuration", "upload_configuration_",
+    "calc_smearedU", "back_prop", "calc_dSdU", "stout_force_", "evaluate_GaugeAction",
 ]
 
 
@@ -644,3 +645,46 @@ def smear(U, smearing, record=False):
     if record:
         return {"configuration": cur, "history": history}
     return cur
+
+
+def calc_smearedU(U, smearing):
+    """calc_smearedU(Uin, nn) (src/smearing/Abstractsmearing.jl:237-314): returns (Uout, Uout_multi) with Uout_multi the
+    outputs of layers 1..n-1 (the tape back_prop needs besides Uin)."""
+    outs = []
+    cur = U
+    for rho in smearing.rhos:
+        out = GaugeConfiguration(U.backend, U.lattice)
+        U.backend.call("gfb_stout_forward", out._h, cur._h, rho, None)
+        outs.append(out)
+        cur = out
+    return cur, outs[:-1]
+
+
+def calc_dSdU(action, U):
+    """calc_dSdUμ! for all four directions (src/action/GaugeActions.jl:95-123) as one configuration-shaped field."""
+    D = GaugeConfiguration(U.backend, U.lattice)
+    U.backend.call("gfb_wilson_dSdU", D._h, U._h, action.wilson_beta())
+    return D
+
+
+def back_prop(dSdU, smearing, Uout_multi, Uin):
+    """back_prop(δL, nn, Uout_multi, Uin) (src/smearing/Abstractsmearing.jl:352-411): pull dS/dU' at the smeared links back
+    through the stout layers to dS/dU at the bare links."""
+    inputs = [Uin] + list(Uout_multi)
+    cur = dSdU
+    for rho, inp in zip(reversed(smearing.rhos), reversed(inputs)):
+        prev = GaugeConfiguration(Uin.backend, Uin.lattice)
+        Uin.backend.call("gfb_stout_backward", prev._h, cur._h, inp._h, rho)
+        cur = prev
+    return cur
+
+
+def stout_force_(P, U, action, smearing, step_size):
+    """The momentum kick of HMC with a stout-smeared action as the user composes it in
+    test/HMCstout_test_nowing.jl:99-118: Uout = calc_smearedU(U); dSdU = calc_dSdUμ(action, Uout);
+    dSdUbare = back_prop(dSdU); P_mu += -step_size/NC * TA(U_mu dSdUbare_mu)."""
+    Uout, multi = calc_smearedU(U, smearing)
+    dS = calc_dSdU(action, Uout)
+    bare = back_prop(dS, smearing, multi, U)
+    U.backend.call("gfb_kick_from_dSdU", P._h, U._h, bare._h, -float(step_size) / 3.0)
+    return P

@@ -575,6 +575,207 @@ void orc_stout_forward(double* Uout, const double* Uin, const int* dims, double 
     }
 }
 
+}  // extern "C"
+
+// ----------------------------------------------------------------------------- stout backward
+
+namespace {
+
+// Pull-back of the matrix exponential, L = C * d exp(Q)/dQ, defined by tr(L dQ) = tr(C d(exp Q)).
+// Route 0 (independent of the reference's closed form): term-by-term derivative of the Taylor
+// series, d(Q^{n+1}) = sum_k Q^k dQ Q^{n-k}  =>  L = sum_n S_n/(n+1)!,  S_0 = C, S_{n+1} = Q S_n + C Q^{n+1}.
+inline M3 exp_pullback_series(const M3& C, const M3& Q) {
+    // scaling keeps the series short and well conditioned: exp(Q) = exp(Q/2^s)^(2^s) is NOT used here
+    // (the derivative of a power is awkward); stout arguments are small, so 60 terms cover |Q| < 8.
+    M3 L = C, S = C, CQn = C;
+    double inv_fact = 1.0;  // 1/(n+1)!
+    for (int n = 0; n < 60; n++) {
+        CQn = mul(CQn, Q);               // C Q^{n+1}
+        S = add(mul(Q, S), CQn);         // S_{n+1}
+        inv_fact /= (double)(n + 2);     // 1/(n+2)!
+        L = add(L, scale(inv_fact, S));
+    }
+    return L;
+}
+
+// Route 1: the reference's closed form (Morningstar-Peardon), CdexpQdQ! for NC=3
+// (src/smearing/stout_fast.jl:888-946, 1031-1081) with calc_coefficients_Q
+// (src/AbstractGaugefields.jl:3284-3343): with Qt = Q/i Hermitian,
+//   L = [ tr(C B1) Qt + tr(C B2) Qt^2 + f1 C + f2 (Qt C + C Qt) ] / i,   B_i = b_i0 + b_i1 Qt + b_i2 Qt^2.
+// Like the reference it returns false (output untouched) when |tr Q^2| <= 1e-18; unlike the reference it
+// reflects c0 < 0 (the reference's formula is only valid for c0 >= 0) so it can be used on any input.
+inline bool exp_pullback_closed(const M3& C, const M3& Q, M3* out) {
+    cd trq2 = trace(mul(Q, Q));
+    if (std::abs(trq2) <= 1e-18) return false;
+    M3 qt = scale(cd(0, -1), Q);
+    M3 qt2 = mul(qt, qt);
+    cd det = qt.a[0][0] * (qt.a[1][1] * qt.a[2][2] - qt.a[1][2] * qt.a[2][1]) - qt.a[0][1] * (qt.a[1][0] * qt.a[2][2] - qt.a[1][2] * qt.a[2][0]) +
+             qt.a[0][2] * (qt.a[1][0] * qt.a[2][1] - qt.a[1][1] * qt.a[2][0]);
+    double c0 = det.real();
+    double c1 = 0.5 * trace(qt2).real();
+    bool reflect = c0 < 0;
+    if (reflect) c0 = -c0;
+    double c0max = 2.0 * std::pow(c1 / 3.0, 1.5);
+    double th = std::acos(std::min(1.0, c0 / c0max));
+    double u = std::sqrt(c1 / 3.0) * std::cos(th / 3.0);
+    double w = std::sqrt(c1) * std::sin(th / 3.0);
+    double w2 = w * w, u2 = u * u;
+    double xi0, xi1;
+    if (std::abs(w) < 0.05) {
+        xi0 = 1.0 - w2 / 6.0 * (1.0 - w2 / 20.0 * (1.0 - w2 / 42.0 * (1.0 - w2 / 72.0)));
+        xi1 = -(1.0 / 3.0 - w2 / 30.0 * (1.0 - w2 / 28.0 * (1.0 - w2 / 54.0)));
+    } else {
+        xi0 = std::sin(w) / w;
+        xi1 = std::cos(w) / w2 - std::sin(w) / (w2 * w);
+    }
+    const cd I(0, 1);
+    cd emiu = std::exp(-I * u), e2iu = std::exp(2.0 * I * u);
+    double cw = std::cos(w);
+    cd h0 = (u2 - w2) * e2iu + emiu * (8.0 * u2 * cw + 2.0 * I * u * (3.0 * u2 + w2) * xi0);
+    cd h1 = 2.0 * u * e2iu - emiu * (2.0 * u * cw - I * (3.0 * u2 - w2) * xi0);
+    cd h2 = e2iu - emiu * (cw + 3.0 * I * u * xi0);
+    double denom = 9.0 * u2 - w2;
+    cd f0 = h0 / denom, f1 = h1 / denom, f2 = h2 / denom;
+    cd r10 = 2.0 * (u + I * (u2 - w2)) * e2iu + 2.0 * emiu * (4.0 * u * (2.0 - I * u) * cw + I * (9.0 * u2 + w2 - I * u * (3.0 * u2 + w2)) * xi0);
+    cd r11 = 2.0 * (1.0 + 2.0 * I * u) * e2iu + emiu * (-2.0 * (1.0 - I * u) * cw + I * (6.0 * u + I * (w2 - 3.0 * u2)) * xi0);
+    cd r12 = 2.0 * I * e2iu + I * emiu * (cw - 3.0 * (1.0 - I * u) * xi0);
+    cd r20 = -2.0 * e2iu + 2.0 * I * u * emiu * (cw + (1.0 + 4.0 * I * u) * xi0 + 3.0 * u2 * xi1);
+    cd r21 = -I * emiu * (cw + (1.0 + 2.0 * I * u) * xi0 - 3.0 * u2 * xi1);
+    cd r22 = emiu * (xi0 - 3.0 * I * u * xi1);
+    double d2 = 2.0 * denom * denom;
+    cd b10 = (2.0 * u * r10 + (3.0 * u2 - w2) * r20 - 2.0 * (15.0 * u2 + w2) * f0) / d2;
+    cd b11 = (2.0 * u * r11 + (3.0 * u2 - w2) * r21 - 2.0 * (15.0 * u2 + w2) * f1) / d2;
+    cd b12 = (2.0 * u * r12 + (3.0 * u2 - w2) * r22 - 2.0 * (15.0 * u2 + w2) * f2) / d2;
+    cd b20 = (r10 - 3.0 * u * r20 - 24.0 * u * f0) / d2;
+    cd b21 = (r11 - 3.0 * u * r21 - 24.0 * u * f1) / d2;
+    cd b22 = (r12 - 3.0 * u * r22 - 24.0 * u * f2) / d2;
+    if (reflect) {  // f_j(-c0,c1) = (-1)^j conj f_j(c0,c1);  b_1j -> (-1)^j conj,  b_2j -> (-1)^(j+1) conj
+        f0 = std::conj(f0); f1 = -std::conj(f1); f2 = std::conj(f2);
+        b10 = std::conj(b10); b11 = -std::conj(b11); b12 = std::conj(b12);
+        b20 = -std::conj(b20); b21 = std::conj(b21); b22 = -std::conj(b22);
+    }
+    M3 B1 = add(add(scale(b10, ident3()), scale(b11, qt)), scale(b12, qt2));
+    M3 B2 = add(add(scale(b20, ident3()), scale(b21, qt)), scale(b22, qt2));
+    cd t1 = trace(mul(C, B1)), t2 = trace(mul(C, B2));
+    M3 r = add(add(scale(t1, qt), scale(t2, qt2)), add(scale(f1, C), scale(f2, add(mul(qt, C), mul(C, qt)))));
+    *out = scale(cd(0, -1), r);
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+// back-propagation through ONE plaquette-staple stout layer with scalar rho
+// (layer_pullback! -> backward_dSdUαUβρ_add!, src/smearing/stout_fast.jl:222-245, 317-407; pieces
+//  calc_dSdu1! :629, calc_dSdQ! :636, calc_dSdΩ! :683, calc_dSdC! :688, calc_dSdUdag! :693,
+//  calc_dSdUν_fromdSCμ_add! :712-785 with the dCμ/dUν, dCμ†/dUν tables of src/smearing/stout_dataset.jl:22-95
+//  expanded by hand for the plaquette staple).
+// Convention (src/molecular_dynamics.jl:255-265): dS = sum tr(D_mu(x) dU_mu(x)) + c.c., D = "dSdU".
+// dOut = dS/dU' (U' = smeared links), dIn = dS/dU.  route: 0 = series pull-back, 1 = closed form.
+void orc_stout_backward(double* dIn, const double* dOut, const double* Uin, const int* dims, double rho, int route) {
+    Lat L(dims);
+    size_t nu = (size_t)4 * L.V * 18;
+    std::vector<double> Lam(nu);  // Lambda_mu(x) = dS/dC_mu(x) = U_mu^dag dS/dOmega_mu
+#pragma omp parallel for
+    for (long s = 0; s < L.V; s++) {
+        int x[4];
+        L.coord(s, x);
+        for (int mu = 0; mu < 4; mu++) {
+            M3 u = getU(Uin, L, mu, s), dp = getU(dOut, L, mu, s);
+            M3 c = scale(rho, staple_sum(Uin, L, x, mu));
+            M3 q = ta_matrix(mul(c, dag(u)));
+            M3 eq = exp_taylor(q);
+            M3 acc = mul(dp, eq);                        // calc_dSdu1!: dS/dU' * exp(Q)
+            M3 cc = mul(u, dp);                          // calc_dSdQ!: C = U * dS/dU'
+            M3 dsdq = zero3();                           // reference leaves the output untouched (zeroed temp) below eps_Q
+            if (route == 1) exp_pullback_closed(cc, q, &dsdq);
+            else dsdq = exp_pullback_series(cc, q);
+            M3 dsdo = ta_matrix(dsdq);                   // calc_dSdΩ!
+            setU(Lam.data(), L, mu, s, mul(dag(u), dsdo));  // calc_dSdC!
+            acc = add(acc, dag(mul(dsdo, c)));           // calc_dSdUdag! then add_U!(dSdU, dSdUdag')
+            setU(dIn, L, mu, s, acc);
+        }
+    }
+    // dS/dC_mu star dC_mu/dU_nu and dS/dC_mu^dag star dC_mu^dag/dU_nu, gathered per target link (y, alpha)
+#pragma omp parallel for
+    for (long s = 0; s < L.V; s++) {
+        int y[4];
+        L.coord(s, y);
+        auto at = [&](int d1, int s1, int d2, int s2) {
+            int z[4] = {y[0], y[1], y[2], y[3]};
+            if (s1) z[d1] = (z[d1] + s1 + L.n[d1]) % L.n[d1];
+            if (s2) z[d2] = (z[d2] + s2 + L.n[d2]) % L.n[d2];
+            return L.idx(z);
+        };
+        for (int al = 0; al < 4; al++) {
+            M3 acc = zero3();
+            for (int be = 0; be < 4; be++) {
+                if (be == al) continue;
+                const int mu = be, nu = al;  // target link plays the role of U_nu in C_mu
+                // (a) U_nu(x) in the upper staple of C_mu(x), x = y
+                acc = add(acc, mul(mul(getU(Uin, L, mu, at(nu, 1, 0, 0)), dag(getU(Uin, L, nu, at(mu, 1, 0, 0)))), getU(Lam.data(), L, mu, s)));
+                // (d) U_nu(x-nu+mu) in the lower staple of C_mu(x), x = y+nu-mu
+                acc = add(acc, mul(getU(Lam.data(), L, mu, at(nu, 1, mu, -1)), mul(dag(getU(Uin, L, nu, at(mu, -1, 0, 0))), getU(Uin, L, mu, at(mu, -1, 0, 0)))));
+                // (e) U_nu(x+mu) in the adjoint upper staple of C_mu(x)^dag, x = y-mu
+                acc = add(acc, mul(mul(dag(getU(Uin, L, mu, at(mu, -1, nu, 1))), dag(getU(Uin, L, nu, at(mu, -1, 0, 0)))), dag(getU(Lam.data(), L, mu, at(mu, -1, 0, 0)))));
+                // (f) U_nu(x-nu) in the adjoint lower staple of C_mu(x)^dag, x = y+nu
+                acc = add(acc, mul(dag(getU(Lam.data(), L, mu, at(nu, 1, 0, 0))), mul(dag(getU(Uin, L, nu, at(mu, 1, 0, 0))), dag(getU(Uin, L, mu, s)))));
+                // target link plays the role of U_mu in C_mu (mu = al), staple direction be
+                const int m = al, n = be;
+                // (b) U_mu(x+nu) in the upper staple of C_mu(x), x = y-n
+                acc = add(acc, mul(mul(dag(getU(Uin, L, n, at(n, -1, m, 1))), getU(Lam.data(), L, m, at(n, -1, 0, 0))), getU(Uin, L, n, at(n, -1, 0, 0))));
+                // (c) U_mu(x-nu) in the lower staple of C_mu(x), x = y+n
+                acc = add(acc, mul(mul(getU(Uin, L, n, at(m, 1, 0, 0)), getU(Lam.data(), L, m, at(n, 1, 0, 0))), dag(getU(Uin, L, n, s))));
+            }
+            setU(dIn, L, al, s, add(getU(dIn, L, al, s), scale(rho, acc)));
+        }
+    }
+}
+
+// calc_dSdUmu! for the Wilson action pushed as beta/2 (plaq + plaq') (src/action/GaugeActions.jl:95-123):
+// D_mu(x) = (beta/2) * sum of the six staples = (beta/2) * V_mu(x)^dagger
+void orc_wilson_dSdU(double* D, const double* U, const int* dims, double beta) {
+    Lat L(dims);
+#pragma omp parallel for
+    for (long s = 0; s < L.V; s++) {
+        int x[4];
+        L.coord(s, x);
+        for (int mu = 0; mu < 4; mu++) setU(D, L, mu, s, scale(beta / 2.0, dag(staple_sum(U, L, x, mu))));
+    }
+}
+
+// P_mu += factor * TAcoeffs(U_mu * D_mu)  (md_force! tail, src/molecular_dynamics.jl:255-265)
+void orc_kick_from_dSdU(double* P, const double* U, const double* D, const int* dims, double factor) {
+    Lat L(dims);
+#pragma omp parallel for
+    for (long s = 0; s < L.V; s++)
+        for (int mu = 0; mu < 4; mu++) {
+            double c[8];
+            ta_coeffs(mul(getU(U, L, mu, s), getU(D, L, mu, s)), c);
+            double* p = P + ((long)mu * L.V + s) * 8;
+            for (int a = 0; a < 8; a++) p[a] += factor * c[a];
+        }
+}
+
+// single-matrix probe of the exp pull-back: C, Q, out in the host layout (column-major 3x3); returns 0 if skipped
+int orc_exp_pullback(const double* c18, const double* q18, int route, double* out18) {
+    M3 C, Q, R = zero3();
+    for (int j = 0; j < 3; j++) for (int i = 0; i < 3; i++) {
+        C.a[i][j] = cd(c18[2 * (i + 3 * j)], c18[2 * (i + 3 * j) + 1]);
+        Q.a[i][j] = cd(q18[2 * (i + 3 * j)], q18[2 * (i + 3 * j) + 1]);
+    }
+    int ok = 1;
+    if (route == 1) ok = exp_pullback_closed(C, Q, &R) ? 1 : 0;
+    else R = exp_pullback_series(C, Q);
+    for (int j = 0; j < 3; j++) for (int i = 0; i < 3; i++) { out18[2 * (i + 3 * j)] = R.a[i][j].real(); out18[2 * (i + 3 * j) + 1] = R.a[i][j].imag(); }
+    return ok;
+}
+
+}  // extern "C"
+
+extern "C" {
+
 // ----------------------------------------------------------------------------- single-matrix probes (unit tests)
 
 void orc_exp_ta(const double* c8, double t, int route, double* out18) {

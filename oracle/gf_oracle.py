@@ -198,3 +198,33 @@ def stout_forward(U, dims, rho, want_q=False):
     Q = new_p(dims) if want_q else None
     lib().orc_stout_forward(_dp(out), _dp(U), _dims(dims), ctypes.c_double(rho), _dp(Q) if want_q else None)
     return (out, Q) if want_q else out
+
+
+def stout_backward(d_out, U, dims, rho, route=0):
+    """back-prop through one stout layer: d_out = dS/dU' -> returns dS/dU (reference dSdU convention)."""
+    d_in = np.empty_like(U)
+    lib().orc_stout_backward(_dp(d_in), _dp(np.ascontiguousarray(d_out)), _dp(U), _dims(dims), ctypes.c_double(rho), ctypes.c_int(route))
+    return d_in
+
+
+def wilson_dSdU(U, dims, beta):
+    """calc_dSdUmu! of the Wilson action pushed as beta/2*(plaq+plaq'): (beta/2) * sum of six staples."""
+    D = np.empty_like(U)
+    lib().orc_wilson_dSdU(_dp(D), _dp(U), _dims(dims), ctypes.c_double(beta))
+    return D
+
+
+def kick_from_dSdU(P, U, D, dims, factor):
+    """P_mu += factor * TAcoeffs(U_mu * D_mu) (md_force! tail)."""
+    lib().orc_kick_from_dSdU(_dp(P), _dp(U), _dp(np.ascontiguousarray(D)), _dims(dims), ctypes.c_double(factor))
+    return P
+
+
+def exp_pullback(C, Q, route=0):
+    """L with tr(L dQ) = tr(C d exp(Q)); C, Q 3x3 in math indexing.  Returns (L, applied)."""
+    c = np.ascontiguousarray(np.asarray(C, dtype=np.complex128).T)
+    q = np.ascontiguousarray(np.asarray(Q, dtype=np.complex128).T)
+    out = np.zeros((3, 3), dtype=np.complex128)
+    lib().orc_exp_pullback.restype = ctypes.c_int
+    ok = lib().orc_exp_pullback(_dp(c), _dp(q), ctypes.c_int(route), _dp(out))
+    return out.T.copy(), bool(ok)

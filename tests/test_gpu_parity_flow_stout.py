@@ -97,3 +97,47 @@ def test_polyakov_loop(backend, oracle):
     got = gfb200.measure_polyakov_loop(U, normalize=False)
     want = oracle.polyakov(Uh, dims)
     assert abs(got - want) < 1e-13
+
+
+def test_stout_backward_matches_oracle(backend, oracle):
+    """back_prop through two stout layers (Abstractsmearing.jl:352-411, stout_fast.jl:317-407) and the resulting
+    HMC force of the smeared Wilson action, against the oracle's chain rule (itself pinned by finite differences
+    and by the reference's closed-form exp pull-back in tests/test_oracle_pins.py)."""
+    import gfb200
+
+    dims = DIMS_ANISO
+    beta, rho = 5.7, 0.1
+    Uh = oracle.hot_start_philox(dims, 2024)
+    for _ in range(2):
+        oracle.flow_step(Uh, dims, 0.02)
+    U = gfb200.gauge_configuration(dims, backend=backend).upload(Uh)
+    loops = gfb200.make_loops_fromname("plaquette")
+    action = gfb200.GaugeAction(U).push(beta / 2, loops + loops.adjoint())
+    sm = gfb200.stout_smearing(U, rho=rho, layers=2)
+    Uout, multi = gfb200.calc_smearedU(U, sm)
+    U1 = oracle.stout_forward(Uh, dims, rho)
+    U2 = oracle.stout_forward(U1, dims, rho)
+    d2 = oracle.wilson_dSdU(U2, dims, beta)
+    dS = gfb200.calc_dSdU(action, Uout)
+    assert np.abs(dS.to_host() - d2).max() < 1e-12 * np.abs(d2).max()
+    bare = gfb200.back_prop(dS, sm, multi, U)
+    d1 = oracle.stout_backward(d2, U1, dims, rho)
+    d0 = oracle.stout_backward(d1, Uh, dims, rho)
+    assert np.abs(bare.to_host() - d0).max() < 1e-11 * np.abs(d0).max()
+    assert np.abs(bare.to_host() - d0).max() < 1e-12 * np.abs(d0).max()
+    # one layer from an arbitrary (non-derivative) input field exercises every term with generic matrices
+    rng = np.random.default_rng(4)
+    dr = rng.normal(size=Uh.shape) + 1j * rng.normal(size=Uh.shape)
+    D = gfb200.GaugeConfiguration(backend, dims).upload(dr)
+    out = gfb200.GaugeConfiguration(backend, dims)
+    backend.call("gfb_stout_backward", out._h, D._h, U._h, 0.12)
+    want = oracle.stout_backward(dr, Uh, dims, 0.12)
+    assert np.abs(out.to_host() - want).max() < 1e-12 * np.abs(want).max()
+    # the composed kick (test/HMCstout_test_nowing.jl:99-118)
+    Ph = oracle.gaussian_momenta(dims, 5, 0)
+    P = gfb200.gauge_momenta(U).upload(Ph)
+    gfb200.stout_force_(P, U, action, sm, 0.05)
+    want_p = oracle.kick_from_dSdU(Ph.copy(), Uh, d0, dims, -0.05 / 3.0)
+    assert np.abs(P.to_host() - want_p).max() < 1e-12 * np.abs(want_p).max()
+    with pytest.raises(ValueError):
+        backend.call("gfb_stout_backward", out._h, out._h, U._h, 0.1)

@@ -216,3 +216,80 @@ def test_stout_forward_properties(oracle):
     assert oracle.plaquette(V, DIMS) > oracle.plaquette(U, DIMS)
     m = oracle.mats(V)
     assert np.abs(m @ m.conj().swapaxes(-1, -2) - np.eye(3)).max() < 1e-13
+
+
+# ------------------------------------------------------------------------------------------------
+# stout backward (src/smearing/stout_fast.jl:317-407, 712-785, 888-946)
+# ------------------------------------------------------------------------------------------------
+def _rand_ta(rng, scale):
+    m = rng.normal(size=(3, 3)) + 1j * rng.normal(size=(3, 3))
+    q = (m - m.conj().T) / 2
+    q -= np.trace(q) / 3 * np.eye(3)
+    return q * scale
+
+
+def test_exp_pullback_series_vs_closed_form_and_fd(oracle):
+    """CdexpQdQ!: the reference's closed form (AbstractGaugefields.jl:3284-3343) against the independent series
+    route (< 1e-11, the bar of test/latticematrices_compat.jl:440-465) and against finite differences of expm."""
+    from scipy.linalg import expm
+
+    rng = np.random.default_rng(3)
+    for scale in (1e-4, 0.05, 0.3, 1.0):
+        for _ in range(6):
+            Q = _rand_ta(rng, scale)
+            C = rng.normal(size=(3, 3)) + 1j * rng.normal(size=(3, 3))
+            L0, _ = oracle.exp_pullback(C, Q, 0)
+            L1, ok = oracle.exp_pullback(C, Q, 1)
+            assert ok
+            # the closed form is derived with the traceless Cayley-Hamilton relation, so it may differ from the
+            # unconstrained derivative by a multiple of the identity, which no traceless dQ can see (and which
+            # calc_dSdΩ!'s projection removes): compare the traceless parts
+            tl = lambda m: m - np.trace(m) / 3 * np.eye(3)
+            assert np.abs(tl(L0) - tl(L1)).max() < 1e-11 * max(1.0, np.abs(L0).max())
+            # tr(L dQ) == tr(C d exp(Q)) for a random direction (central difference)
+            dQ = _rand_ta(rng, 1.0)
+            h = 1e-5
+            fd = np.trace(C @ (expm(Q + h * dQ) - expm(Q - h * dQ))) / (2 * h)
+            assert abs(np.trace(L0 @ dQ) - fd) < 1e-8 * max(1.0, abs(fd))
+    # the reference skips (leaves the output untouched) below |tr Q^2| = 1e-18
+    _, ok = oracle.exp_pullback(np.eye(3), np.zeros((3, 3)), 1)
+    assert not ok
+    L0, _ = oracle.exp_pullback(np.eye(3) * 2.0, np.zeros((3, 3)), 0)
+    assert np.allclose(L0, np.eye(3) * 2.0)
+
+
+def test_stout_backward_against_finite_differences(oracle):
+    """dS/dU through two stout layers: the chain-rule result, fed to the md_force! tail, must equal the
+    directional derivative of S(U) = -(beta/3) sum Re tr P[stout(stout(U))] (pattern: stout_fast.jl:787-886)."""
+    dims = (4, 4, 2, 2)
+    beta, rho = 5.7, 0.1
+    U = oracle.hot_start_philox(dims, 21)
+    for _ in range(2):
+        oracle.flow_step(U, dims, 0.02)
+
+    def action(Uin):
+        V = oracle.stout_forward(oracle.stout_forward(Uin, dims, rho), dims, rho)
+        return -(beta / 3.0) * oracle.plaquette_sum(V, dims)
+
+    U1 = oracle.stout_forward(U, dims, rho)
+    U2 = oracle.stout_forward(U1, dims, rho)
+    d2 = oracle.wilson_dSdU(U2, dims, beta)
+    for route in (0, 1):
+        d1 = oracle.stout_backward(d2, U1, dims, rho, route)
+        d0 = oracle.stout_backward(d1, U, dims, rho, route)
+        F = oracle.kick_from_dSdU(oracle.new_p(dims), U, d0, dims, -1.0 / 3.0)  # force = -(1/NC) TA(U dSdU)
+        # d/ds S(exp(s X) U)|_0 with X = sum_a x_a i lambda_a/2 equals -sum_a x_a F_a (dP/dt = F = -dS/dX)
+        rng = np.random.default_rng(9)
+        X = rng.normal(size=oracle.p_shape(dims))
+        h = 1e-5
+        Sp = action(oracle.update_links(U, X, dims, +h))
+        Sm = action(oracle.update_links(U, X, dims, -h))
+        fd = (Sp - Sm) / (2 * h)
+        an = -float(np.sum(X * F))
+        assert abs(fd - an) < 2e-7 * max(1.0, abs(an)), (route, fd, an)
+    # with rho = 0 the layer is the identity and back-prop returns its input
+    d = oracle.stout_backward(d2, U, dims, 0.0, 0)
+    assert np.abs(d - d2).max() < 1e-14
+    # unsmeared consistency: kick from wilson_dSdU == md_force!
+    F0 = oracle.kick_from_dSdU(oracle.new_p(dims), U, oracle.wilson_dSdU(U, dims, beta), dims, -1.0 / 3.0)
+    assert np.abs(F0 - oracle.force(U, dims, beta)).max() < 1e-13
