@@ -26,6 +26,7 @@ Geom make_geom(const gfb_ctx* ctx, int nx, int ny, int nz, int nt, int slab_glob
     g.tloc = nt / G;
     g.v3 = nx * ny * nz;
     g.nt = nt;
+    g.t_stride = 1;
     g.t0 = slab_global_index * g.tloc;
     if (G > 1) {
         g.t_up_wrap = g.tloc;
@@ -81,7 +82,13 @@ static int ensure_staging(gfb_ctx* ctx, Slab& s, size_t bytes) {
 static int init_slab(gfb_ctx* ctx, Slab& s) {
     GFB_CUDA(ctx, cudaSetDevice(s.device));
     GFB_CUDA(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-    GFB_CUDA(ctx, cudaStreamCreateWithFlags(&s.comm_stream, cudaStreamNonBlocking));
+    {
+        // the halo stream outranks the compute stream so that the NCCL send/recv kernels get SM slots while a large
+        // interior grid is resident
+        int lo = 0, hi = 0;
+        GFB_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        GFB_CUDA(ctx, cudaStreamCreateWithPriority(&s.comm_stream, cudaStreamNonBlocking, hi));
+    }
     GFB_CUDA(ctx, cudaEventCreateWithFlags(&s.ev_a, cudaEventDisableTiming));
     GFB_CUDA(ctx, cudaEventCreateWithFlags(&s.ev_b, cudaEventDisableTiming));
     GFB_CUDA(ctx, cudaEventCreateWithFlags(&s.ev_c, cudaEventDisableTiming));
@@ -123,15 +130,26 @@ static int gather_scalars(gfb_ctx* ctx, int nslots, double* out) {
 // t-halo exchange of `buf` (layout of gfb_gauge::d) on the compute streams: slot tloc <- next slab's
 // slice 0, slot tloc+1 <- previous slab's last slice (set_wing_U!/set_halo! in the
 // reference, gaugefields_4D_MPILattice.jl:497-507).
-static int exchange_halo_buffers(gfb_ctx* ctx, const gfb_gauge* g, const std::vector<double2*>& buf, bool on_comm_stream) {
+// overlapped = false: on the compute streams (in stream order with everything else).
+// overlapped = true : on the high-priority halo streams, after the work already queued on the compute streams (the
+//   boundary time-slices); ev_b marks completion and the caller makes the compute stream wait on it only AFTER it has
+//   queued the interior slices, so the exchange over NVLink runs concurrently with the interior compute.
+static int exchange_halo_buffers(gfb_ctx* ctx, const gfb_gauge* g, const std::vector<double2*>& buf, bool overlapped) {
     const int G = ctx->nslabs_total;
     if (G == 1) return GFB_OK;
     const size_t slice = g->slice_elems() * 2;  // doubles
     const size_t up_count = (size_t)27 * g->nx * g->ny * g->nz * 2;  // the t+1 halo only needs the three spatial links
+    if (overlapped) {
+        for (auto& s : ctx->slabs) {
+            GFB_CUDA(ctx, cudaSetDevice(s.device));
+            GFB_CUDA(ctx, cudaEventRecord(s.ev_a, s.stream));
+            GFB_CUDA(ctx, cudaStreamWaitEvent(s.comm_stream, s.ev_a, 0));
+        }
+    }
     GFB_NCCL(ctx, ncclGroupStart());
     for (size_t i = 0; i < ctx->slabs.size(); i++) {
         Slab& s = ctx->slabs[i];
-        cudaStream_t st = on_comm_stream ? s.comm_stream : s.stream;
+        cudaStream_t st = overlapped ? s.comm_stream : s.stream;
         const int prev = (s.index + G - 1) % G, next = (s.index + 1) % G;
         double* base = reinterpret_cast<double*>(buf[i]);
         double* first = base;
@@ -144,6 +162,21 @@ static int exchange_halo_buffers(gfb_ctx* ctx, const gfb_gauge* g, const std::ve
         GFB_NCCL(ctx, ncclRecv(dn, slice, ncclDouble, prev, s.nccl, st));
     }
     GFB_NCCL(ctx, ncclGroupEnd());
+    if (overlapped) {
+        for (auto& s : ctx->slabs) {
+            GFB_CUDA(ctx, cudaSetDevice(s.device));
+            GFB_CUDA(ctx, cudaEventRecord(s.ev_b, s.comm_stream));
+        }
+    }
+    return GFB_OK;
+}
+// compute streams wait for the overlapped exchange started last
+static int join_halo_exchange(gfb_ctx* ctx) {
+    if (ctx->nslabs_total == 1) return GFB_OK;
+    for (auto& s : ctx->slabs) {
+        GFB_CUDA(ctx, cudaSetDevice(s.device));
+        GFB_CUDA(ctx, cudaStreamWaitEvent(s.stream, s.ev_b, 0));
+    }
     return GFB_OK;
 }
 static int ensure_halo(gfb_gauge* g) {
@@ -675,18 +708,30 @@ int gfb_polyakov(gfb_gauge* g, double* out2) {
 }
 
 // ---- updates -----------------------------------------------------------------------------------------
-// one fused pass over all local slabs: Z' = a*TA(U V^dag) + b*Z ; Uout = exp(c Z') Uin
+// one fused pass over all local slabs: Z' = a*TA(U V^dag) + b*Z ; Uout = exp(c Z') Uin.
+// With several slabs and an output link field the pass is ordered boundary slices -> halo exchange of the OUTPUT
+// (halo stream) || interior slices -> join, so on return (in stream order) uout's halo slots are valid.
 static int fused_pass(gfb_gauge* g, const std::vector<double2*>& uin, const std::vector<double2*>* uout, const std::vector<double*>* zin,
                       const std::vector<double*>* zout, const FusedArgs& fa) {
     gfb_ctx* ctx = g->ctx;
-    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+    const bool split = ctx->nslabs_total > 1 && uout != nullptr;
+    auto launch = [&](size_t i, int t0, int tc, int stride = 1) -> int {
         Slab& s = ctx->slabs[i];
         GFB_CUDA(ctx, cudaSetDevice(s.device));
         Geom geo = geom_of(g, i);
-        launch_force_fused(s.stream, geo, 0, geo.tloc, uin[i], uout ? (*uout)[i] : nullptr, zin ? (*zin)[i] : nullptr, zout ? (*zout)[i] : nullptr, fa);
-        GFB_CHECK(post_launch(ctx));
+        geo.t_stride = stride;
+        if (tc <= 0) return GFB_OK;
+        launch_force_fused(s.stream, geo, t0, tc, uin[i], uout ? (*uout)[i] : nullptr, zin ? (*zin)[i] : nullptr, zout ? (*zout)[i] : nullptr, fa);
+        return post_launch(ctx);
+    };
+    if (!split) {
+        for (size_t i = 0; i < ctx->slabs.size(); i++) GFB_CHECK(launch(i, 0, g->tloc));
+        return GFB_OK;
     }
-    return GFB_OK;
+    for (size_t i = 0; i < ctx->slabs.size(); i++) GFB_CHECK(launch(i, 0, 2, g->tloc - 1));  // slices 0 and tloc-1 in one launch
+    GFB_CHECK(exchange_halo_buffers(ctx, g, *uout, true));
+    for (size_t i = 0; i < ctx->slabs.size(); i++) GFB_CHECK(launch(i, 1, g->tloc - 2));
+    return join_halo_exchange(ctx);
 }
 
 int gfb_force(gfb_mom* f, gfb_gauge* g, double beta) {
@@ -724,12 +769,27 @@ int gfb_update_links(gfb_gauge* g, const gfb_mom* p, double eps) {
     gfb_ctx* ctx = g->ctx;
     if (!same_shape(g, p)) return fail(ctx, GFB_ERR_ARG, "U and P must have the same lattice");
     if (!std::isfinite(eps)) return fail(ctx, GFB_ERR_ARG, "the gauge-field step size must be finite");
-    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+    const bool split = ctx->nslabs_total > 1;
+    auto launch = [&](size_t i, int t0, int tc, int stride = 1) -> int {
         GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
-        launch_update_links(ctx->slabs[i].stream, geom_of(g, i), g->d[i], g->d[i], p->d[i], eps);
-        GFB_CHECK(post_launch(ctx));
+        if (tc <= 0) return GFB_OK;
+        Geom geo = geom_of(g, i);
+        geo.t_stride = stride;
+        launch_update_links(ctx->slabs[i].stream, geo, t0, tc, g->d[i], g->d[i], p->d[i], eps);
+        return post_launch(ctx);
+    };
+    if (!split) {
+        for (size_t i = 0; i < ctx->slabs.size(); i++) GFB_CHECK(launch(i, 0, g->tloc));
+        g->halo_valid = false;
+        return GFB_OK;
     }
-    g->halo_valid = false;
+    // site-local update: boundary slices first, their exchange overlaps the interior (set_wing_U!/set_halo! of the
+    // reference happens inside substitute_U!, gaugefields_4D_MPILattice.jl:497-512)
+    for (size_t i = 0; i < ctx->slabs.size(); i++) GFB_CHECK(launch(i, 0, 2, g->tloc - 1));
+    GFB_CHECK(exchange_halo_buffers(ctx, g, g->d, true));
+    for (size_t i = 0; i < ctx->slabs.size(); i++) GFB_CHECK(launch(i, 1, g->tloc - 2));
+    GFB_CHECK(join_halo_exchange(ctx));
+    g->halo_valid = true;
     return GFB_OK;
 }
 int gfb_exp_aF_U(gfb_gauge* w, double a, const gfb_mom* f, const gfb_gauge* u) {
@@ -739,7 +799,7 @@ int gfb_exp_aF_U(gfb_gauge* w, double a, const gfb_mom* f, const gfb_gauge* u) {
     if (a == 0.0) return fail(ctx, GFB_ERR_ARG, "the step must not be zero in exp_aF_U");
     for (size_t i = 0; i < ctx->slabs.size(); i++) {
         GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
-        launch_update_links(ctx->slabs[i].stream, geom_of(w, i), u->d[i], w->d[i], f->d[i], a);
+        launch_update_links(ctx->slabs[i].stream, geom_of(w, i), 0, w->tloc, u->d[i], w->d[i], f->d[i], a);
         GFB_CHECK(post_launch(ctx));
     }
     w->halo_valid = false;
@@ -784,7 +844,7 @@ int gfb_md_trajectory(gfb_gauge* g, gfb_mom* p, double beta, int steps, double t
                 fa.c = (k == steps - 1) ? eps / 2 : eps;
                 GFB_CHECK(fused_pass(g, g->d, &ws->alt, &p->d, &p->d, fa));
                 std::swap(g->d, ws->alt);
-                g->halo_valid = false;
+                g->halo_valid = true;  // exchanged inside the pass, overlapped with the interior slices
             }
         } else {
             for (int k = 0; k < steps; k++) {
@@ -793,7 +853,7 @@ int gfb_md_trajectory(gfb_gauge* g, gfb_mom* p, double beta, int steps, double t
                 fa.c = eps;
                 GFB_CHECK(fused_pass(g, g->d, &ws->alt, &p->d, &p->d, fa));
                 std::swap(g->d, ws->alt);
-                g->halo_valid = false;
+                g->halo_valid = true;  // exchanged inside the pass, overlapped with the interior slices
             }
             GFB_CHECK(gfb_update_momenta(p, g, eps / 2, beta));
         }
@@ -819,15 +879,15 @@ int gfb_flow(gfb_gauge* g, double eps, int nsteps) {
         GFB_CHECK(ensure_halo(g));
         fa.a = -eps; fa.b = 0.0; fa.c = 0.25; fa.read_z = false;
         GFB_CHECK(fused_pass(g, g->d, &ws->alt, nullptr, &ws->z, fa));
-        std::swap(g->d, ws->alt); g->halo_valid = false;
+        std::swap(g->d, ws->alt); g->halo_valid = true;
         GFB_CHECK(ensure_halo(g));
         fa.a = -(8.0 / 9.0) * eps; fa.b = -17.0 / 36.0; fa.c = 1.0; fa.read_z = true;
         GFB_CHECK(fused_pass(g, g->d, &ws->alt, &ws->z, &ws->z, fa));
-        std::swap(g->d, ws->alt); g->halo_valid = false;
+        std::swap(g->d, ws->alt); g->halo_valid = true;
         GFB_CHECK(ensure_halo(g));
         fa.a = -(3.0 / 4.0) * eps; fa.b = -1.0; fa.c = 1.0; fa.read_z = true;
         GFB_CHECK(fused_pass(g, g->d, &ws->alt, &ws->z, &ws->z, fa));
-        std::swap(g->d, ws->alt); g->halo_valid = false;
+        std::swap(g->d, ws->alt); g->halo_valid = true;
     }
     return GFB_OK;
 }
@@ -842,7 +902,7 @@ int gfb_stout_forward(gfb_gauge* out, gfb_gauge* in, double rho, gfb_mom* q) {
     FusedArgs fa;
     fa.a = -rho; fa.c = 1.0; fa.do_exp = true; fa.write_z = (q != nullptr);
     GFB_CHECK(fused_pass(in, in->d, &out->d, nullptr, q ? &q->d : nullptr, fa));
-    out->halo_valid = false;
+    out->halo_valid = true;
     return GFB_OK;
 }
 

@@ -61,6 +61,7 @@ void launch_force_fused(cudaStream_t st, const Geom& g, int t_begin, int t_count
     const int SITES = 32;
     dim3 block(SITES, 4);
     long nsites = (long)g.v3 * t_count;
+    if (nsites <= 0) return;
     dim3 grid((unsigned)((nsites + SITES - 1) / SITES));
 #define GFB_LAUNCH_FF(R, W, E) k_force_fused<R, W, E><<<grid, block, 0, st>>>(g, t_begin, t_count, uin, uout, zin, zout, fa.a, fa.b, fa.c)
     if (fa.read_z) {
@@ -79,13 +80,13 @@ void launch_force_fused(cudaStream_t st, const Geom& g, int t_begin, int t_count
 // link update  Uout_mu = exp(c * Z_mu) * Uin_mu  (update_gaugefields!, molecular_dynamics.jl:513-531;
 // exp_aF_U!, AbstractGaugefields.jl:2810-2841).  Site-local, so uout may alias uin.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_update_links(Geom g, const double2* uin, double2* uout, const double* __restrict__ z, double c) {
+__global__ void __launch_bounds__(256) k_update_links(Geom g, int t_begin, int t_count, const double2* uin, double2* uout, const double* __restrict__ z, double c) {
     const int mu = blockIdx.y;
     const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= (long)g.v3 * g.tloc) return;
+    if (n >= (long)g.v3 * t_count) return;
     Coord x;
-    x.t = (int)(n / g.v3);
-    int s3 = (int)(n - (long)x.t * g.v3);
+    x.t = t_begin + (int)(n / g.v3) * g.t_stride;
+    int s3 = (int)(n % g.v3);
     const size_t zo = (size_t)(x.t * 32 + mu * 8) * g.v3 + s3;
     double zz[8];
 #pragma unroll
@@ -99,10 +100,11 @@ __global__ void __launch_bounds__(256) k_update_links(Geom g, const double2* uin
 #pragma unroll
     for (int k = 0; k < 9; k++) uout[uo + (size_t)k * g.v3] = r.e[k];
 }
-void launch_update_links(cudaStream_t st, const Geom& g, const double2* uin, double2* uout, const double* z, double c) {
-    long n = (long)g.v3 * g.tloc;
+void launch_update_links(cudaStream_t st, const Geom& g, int t_begin, int t_count, const double2* uin, double2* uout, const double* z, double c) {
+    long n = (long)g.v3 * t_count;
+    if (n <= 0) return;
     dim3 grid((unsigned)((n + 255) / 256), 4);
-    k_update_links<<<grid, 256, 0, st>>>(g, uin, uout, z, c);
+    k_update_links<<<grid, 256, 0, st>>>(g, t_begin, t_count, uin, uout, z, c);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -23,6 +23,7 @@ struct Geom {
     int t0;                // global t of local slice 0
     int nt;                // global NT
     int nslots;            // tloc (+2 with halo)
+    int t_stride;          // launch covers slices t_begin + j*t_stride, j < t_count (1 = contiguous; tloc-1 = the two boundary slices)
 };
 
 struct Coord {
@@ -37,7 +38,7 @@ __device__ __forceinline__ Coord decode_site(const Geom& g, long n, int t_begin,
     c.x = (int)(n % g.nx); n /= g.nx;
     c.y = (int)(n % g.ny); n /= g.ny;
     int zi = (int)(n % g.zc); n /= g.zc;
-    c.t = t_begin + (int)(n % t_count);
+    c.t = t_begin + (int)(n % t_count) * g.t_stride;
     int zo = (int)(n / t_count);
     c.z = zo * g.zc + zi;
     return c;

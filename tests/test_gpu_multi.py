@@ -72,6 +72,22 @@ def test_two_slabs_match_oracle(backend2, oracle):
     out = gfb200.smear(U, gfb200.stout_smearing(U, rho=0.1, layers=2))
     want = oracle.stout_forward(oracle.stout_forward(Uh, dims, 0.1), dims, 0.1)
     assert np.abs(out.to_host() - want).max() < 1e-12
+    # stout backward across the slab faces (halo of U and of Lambda)
+    sm = gfb200.stout_smearing(U, rho=0.1, layers=2)
+    Uout, multi = gfb200.calc_smearedU(U, sm)
+    bare = gfb200.back_prop(gfb200.calc_dSdU(action, Uout), sm, multi, U)
+    U1 = oracle.stout_forward(Uh, dims, 0.1)
+    d0 = oracle.stout_backward(oracle.stout_backward(oracle.wilson_dSdU(want, dims, 5.7), U1, dims, 0.1), Uh, dims, 0.1)
+    assert np.abs(bare.to_host() - d0).max() < 1e-12 * np.abs(d0).max()
+    # unfused primitives with the overlapped exchange: link update then force on the fresh halo
+    U.upload(Uh)
+    Ph = oracle.gaussian_momenta(dims, 3, 0)
+    P = gfb200.gauge_momenta(U).upload(Ph)
+    md = gfb200.md_driver(U, action, steps=4)
+    gfb200.update_gaugefields_(U, P, 0.1, md)
+    gfb200.md_force_(F, action, U)
+    Fw = oracle.force(oracle.update_links(Uh, Ph, dims, 0.1), dims, 5.7)
+    assert np.abs(F.to_host() - Fw).max() / np.abs(Fw).max() < 1e-12
 
 
 def test_random_fields_are_decomposition_independent(backend2, backend):
