@@ -9,9 +9,11 @@
 A "step" is one QPQ molecular-dynamics step (md_step!, src/molecular_dynamics.jl:611-616) of the
 quenched Wilson action over the whole lattice.  The timed region is ONE gfb_md_trajectory call of
 exactly K steps (diagnostics off), device-timed with CUDA events on the library's compute stream,
-bracketed by barrier + device synchronize, max over ranks.  Workload: synthetic hot start (seed 1234),
-Gaussian momenta (seed 0x5678), 32^3 x 32 sites per GPU (weak scaling: global lattice 32^3 x 32N,
-t-slab decomposition).  The link field (604 MB per GPU) is larger than L2 (126 MB), so no flush is needed.
+bracketed by barrier + device synchronize, max over ranks.  Workload (BASELINE.json configs[4], the lattice the
+metric and the north-star target are quoted on): synthetic hot start (seed 1234), Gaussian momenta (seed 0x5678),
+beta = 6.2, GLOBAL lattice 64^4 split into t-slabs over the N GPUs (strong scaling; 64^4 fits one B200: 24 GB).
+`--scaling weak --lattice X,Y,Z,T` keeps X*Y*Z*T sites PER GPU instead.  The link field (9.7 GB / N per GPU) is larger
+than L2 (126 MB), so no flush is needed.
 """
 import argparse
 import json
@@ -34,8 +36,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--lattice", default="32,32,32,32", help="per-GPU local lattice NX,NY,NZ,T_loc (global NT = T_loc * gpus)")
-    ap.add_argument("--beta", type=float, default=6.0)
+    ap.add_argument("--lattice", default="64,64,64,64", help="NX,NY,NZ,NT: the global lattice (strong) or the per-GPU lattice (weak)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--beta", type=float, default=6.2)
     ap.add_argument("--tau", type=float, default=1.0)
     ap.add_argument("--unfused", action="store_true", help="issue the reference's op sequence (link, kick, link) per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -54,44 +57,62 @@ def measured_peak():
 
 
 class ClockSampler:
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock + throttle reasons of this rank's GPU, polled through NVML from a thread every ~2 ms so that even a
+    timed region of a few hundred ms is covered (nvidia-smi -lms cannot go that fast)."""
 
-    def __init__(self):
-        self.proc, self.path = None, "/tmp/gfb_clocks_%d.csv" % os.getpid()
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+
+    def __init__(self, index=0):
+        self.index, self.samples, self.stop_flag, self.thread, self.err = index, [], False, None, None
+
+    def _run(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.smax = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:
+                    pw = None
+                self.samples.append((self.window, sm, rs, pw))
+                time.sleep(0.002)
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
 
     def start(self):
-        try:
-            self.fh = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.fh, stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+        import threading
+
+        self.window = False
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def mark(self, on):
+        self.window = on
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        self.proc.wait()
-        self.fh.close()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in open(self.path):
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); smax.append(float(f[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=2.0)
+        inwin = [x for x in self.samples if x[0]] or self.samples
+        if not inwin:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML samples: %s" % self.err]}
+        sm = sorted(x[1] for x in inwin)
+        reasons = set()
+        for _, _, rs, _ in inwin:
+            for n, b in self.BITS.items():
+                if rs & b:
                     reasons.add(n)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        # samples under load = upper half of the observed clocks (the sampler also sees idle gaps)
-        sm.sort()
-        load = sm[len(sm) // 2:]
-        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
+        pw = [x[3] for x in inwin if x[3] is not None]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": getattr(self, "smax", None), "reasons": sorted(reasons), "samples": len(inwin),
+                "power_w_max": max(pw) if pw else None, "how": "NVML polled every 2 ms during the timed region"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -139,16 +160,22 @@ def cpu_md_steps_per_s(dims_global, beta, tau, steps, warmup, budget_s):
     return value, dt / steps * 1e3 / scale, {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
 
-def run_reference(args, dims_global, rank, world):
+def workload_name(args, dims_global, dims_local):
+    return "SU(3) Wilson QPQ HMC, beta=%g, hot start seed 1234, global lattice %s, %s scaling (%s per GPU, t-slabs)" % (
+        args.beta, "x".join(map(str, dims_global)), args.scaling, "x".join(map(str, dims_local)))
+
+
+def run_reference(args, dims_global, dims_local, rank, world):
     if rank != 0:
         return
     value, ms, cb = cpu_md_steps_per_s(dims_global, args.beta, args.tau, args.steps, args.warmup, budget_s=150.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "SU(3) Wilson QPQ HMC, beta=%g, hot start, lattice %s (32^3x32 per GPU)" % (args.beta, "x".join(map(str, dims_global))),
-                   "note": "CPU oracle port of the reference's serial math (reference is Julia + un-vendored LatticeMatrices.jl; not buildable here)"},
+        "config": {"workload": workload_name(args, dims_global, dims_local),
+                   "note": "CPU oracle port of the reference's serial math, all host cores (OpenMP); the reference is Julia + un-vendored "
+                           "LatticeMatrices.jl and cannot be built in this image (DESIGN.md section 7)"},
         "cpu_baseline": cb,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -161,11 +188,18 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    nx, ny, nz, tl = [int(v) for v in args.lattice.split(",")]
-    dims_global = (nx, ny, nz, tl * max(args.gpus, 1))
+    nx, ny, nz, nt = [int(v) for v in args.lattice.split(",")]
+    ngp = max(args.gpus, 1)
+    if args.scaling == "weak":
+        dims_global, tl = (nx, ny, nz, nt * ngp), nt
+    else:
+        if nt % ngp:
+            raise SystemExit("NT must be divisible by the number of GPUs")
+        dims_global, tl = (nx, ny, nz, nt), nt // ngp
+    dims_local = (nx, ny, nz, tl)
 
     if args.impl == "reference":
-        run_reference(args, dims_global, rank, world)
+        run_reference(args, dims_global, dims_local, rank, world)
         return
 
     import numpy as np
@@ -182,8 +216,9 @@ def main():
     import gfb200
 
     backend = gfb200.B200Backend(ngpu=1, devices=[local_rank], distributed=(world > 1))
-    K, W = args.steps, max(args.warmup, 0)
-    sites_global = nx * ny * nz * tl * world
+    K, W = args.steps, max(args.warmup, 3)
+    sites_global = dims_global[0] * dims_global[1] * dims_global[2] * dims_global[3]
+    sites_local = nx * ny * nz * tl
 
     U = gfb200.gauge_configuration(dims_global, backend=backend, start="hot", seed=1234)
     P = gfb200.gaussian_momenta(U, seed=0x5678, sweep=0)
@@ -198,26 +233,29 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(W, 1)):
-        gfb200.md_trajectory_(U, P, md_w, diagnostics=False)  # one untimed MD step each
-    barrier()
-    sampler = ClockSampler()
+    sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(W):
+        gfb200.md_trajectory_(U, P, md_w, diagnostics=False)  # one untimed MD step each
+    barrier()
     # ---- timed region: exactly K MD steps --------------------------------------------------------
     n0 = backend.kernel_launches()
     barrier()
+    sampler.mark(True)
     backend.tic()
     gfb200.md_trajectory_(U, P, md, diagnostics=False)
     ms = backend.toc()
     barrier()
+    sampler.mark(False)
     launches = backend.kernel_launches() - n0
     if dist is not None:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
     # ---- dominant kernel: average duration of the fused kick+drift launch --------------------------
-    # the K-step trajectory is K fused launches plus one half-drift launch (update_links); time that one
+    # the K-step trajectory is K fused passes plus one half-drift (update_links); time that one
     # alone and subtract, so achieved = algorithmic bytes per launch / average launch duration
     t_extra = 0.0
     if not args.unfused:
@@ -227,9 +265,7 @@ def main():
             gfb200.update_gaugefields_(U, P, 1e-9)
         t_extra = backend.toc() / reps
         barrier()
-    clocks = sampler.stop() if rank == 0 else None
     peak, peak_src = measured_peak()
-    sites_local = nx * ny * nz * tl
     if args.unfused:
         kern, kern_bytes = "k_update_links + k_force_fused<kick> + k_update_links (whole QPQ step)", (2 * (P_BYTES + 2 * U_BYTES) + U_BYTES + 2 * P_BYTES)
         kern_ms = ms / K
@@ -242,8 +278,7 @@ def main():
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
-            traffic = tj.get("k_force_fused_bytes_per_site", None)
-            traffic = traffic * sites_local if traffic is not None and tj.get("lattice") == args.lattice else None
+            traffic = tj["k_force_fused_bytes_per_site"] * sites_local  # ncu dram bytes per site (measured at tj["lattice"]) x this launch's sites
         except Exception:
             traffic = None
 
@@ -275,7 +310,7 @@ def main():
             dt = float(t.item())
         bytes_dir = sites_local * (U_BYTES + P_BYTES) * world
         e2e = {"value": K / dt, "unit": UNIT, "h2d_bytes_per_step": bytes_dir / K, "d2h_bytes_per_step": (bytes_dir + 16) / K,
-               "call": "upload U,P (host, gathered layout) -> md_trajectory!(%d QPQ steps, diagnostics) -> download U,P" % K,
+               "call": "upload U,P (pinned host, reference gathered layout) -> md_trajectory!(%d QPQ steps, diagnostics) -> download U,P" % K,
                "delta_hamiltonian": res.delta_hamiltonian}
 
     cpu_baseline = None
@@ -285,19 +320,19 @@ def main():
     if rank == 0:
         step_bytes = (2 * U_BYTES + 2 * P_BYTES) if not args.unfused else 3904
         line = {
-            "metric": METRIC, "value": K / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 1),
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "metric": METRIC, "value": K / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": "SU(3) Wilson QPQ HMC, beta=%g, hot start seed 1234, lattice %s (%s per GPU, t-slabs)" % (args.beta, "x".join(map(str, dims_global)), "x".join(map(str, (nx, ny, nz, tl)))),
+                "workload": workload_name(args, dims_global, dims_local),
                 "integrator": "QPQ, %s" % ("reference op sequence (link, kick, link)" if args.unfused else "fused kick+drift kernel, adjacent half drifts merged"),
                 "l2": "inputs larger than L2 (links %.0f MB per GPU), no flush" % (sites_local * U_BYTES / 1e6),
                 "link_updates_per_s": 4.0 * sites_global * K / (ms * 1e-3),
                 "algorithmic_bytes_per_site_per_step": step_bytes,
-                "hbm_roofline_frac_of_8TBs": step_bytes * sites_local / (ms / K * 1e-3) / 8e12,
+                "hbm_roofline_frac_of_8TBs_per_gpu": step_bytes * sites_local / (ms / K * 1e-3) / 8e12,
             },
             "roofline": {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel_ms": kern_ms,
-                         "note": "fp64 DFMA issue co-limits this kernel (about 1.4 kDFMA per link); see DESIGN.md"},
+                         "traffic": traffic, "peak_source": peak_src, "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": kern_bytes * sites_local,
+                         "note": "fp64 DFMA issue co-limits this kernel (about 1.6 kDFMA per link); see DESIGN.md section 3"},
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,
             "gpu_launches": int(launches) * world,
