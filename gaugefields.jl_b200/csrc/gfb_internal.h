@@ -85,6 +85,9 @@ struct FusedArgs {
 };
 void launch_force_fused(cudaStream_t st, const Geom& g, int t_begin, int t_count, const double2* uin, double2* uout, const double* zin, double* zout,
                         const FusedArgs& fa);
+// persistent TMA row-tile variant of launch_force_fused (rowtile.cu); false = geometry not covered, nothing launched
+bool launch_rowtile_fused(cudaStream_t st, const Geom& g, int t_begin, int t_count, const double2* uin, double2* uout, const double* zin, double* zout,
+                          const FusedArgs& fa);
 void launch_update_links(cudaStream_t st, const Geom& g, int t_begin, int t_count, const double2* uin, double2* uout, const double* z, double c);
 void launch_plaquette(cudaStream_t st, const Geom& g, const double2* u, double* partial, int* nblocks);
 void launch_sumsq(cudaStream_t st, const double* p, size_t n, double* partial, int* nblocks);

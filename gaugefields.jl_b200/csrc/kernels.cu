@@ -13,6 +13,12 @@
 #ifndef GFB_FF_MINBLOCKS
 #define GFB_FF_MINBLOCKS 4
 #endif
+#ifndef GFB_FF_L2PF
+#define GFB_FF_L2PF 0  // >0: each block bulk-prefetches into L2 the first-touch data (t+1 links, momenta) of the block this many blocks ahead
+#endif
+#ifndef GFB_FF_ROWS
+#define GFB_FF_ROWS 1  // x-rows (32-site groups) per block: neighbouring rows share staple operands through L1
+#endif
 
 namespace gfb {
 
@@ -26,11 +32,35 @@ namespace gfb {
 // (stout_fast.jl:250-274).
 // ------------------------------------------------------------------------------------------------
 template <bool READ_Z, bool WRITE_Z, bool DO_EXP>
-__global__ void __launch_bounds__(128, GFB_FF_MINBLOCKS)
+__global__ void __launch_bounds__(128 * GFB_FF_ROWS, (GFB_FF_MINBLOCKS / GFB_FF_ROWS) > 0 ? (GFB_FF_MINBLOCKS / GFB_FF_ROWS) : 1)
 k_force_fused(Geom g, int t_begin, int t_count, const double2* __restrict__ uin, double2* __restrict__ uout, const double* __restrict__ zin,
               double* __restrict__ zout, double a, double b, double c) {
     const int mu = threadIdx.y;
-    const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long n = ((long)blockIdx.x * GFB_FF_ROWS + threadIdx.z) * blockDim.x + threadIdx.x;
+#if GFB_FF_L2PF > 0
+    if (threadIdx.x == 0 && threadIdx.z == 0) {
+        // DRAM -> L2 ahead of the sweep: the first touch of a time-slice is the "+t" neighbour access, and of the momenta the
+        // kick itself.  One bulk prefetch per 512-byte plane row, issued by one lane per direction.
+        const long np = ((long)blockIdx.x + GFB_FF_L2PF) * GFB_FF_ROWS * 32;
+        if (np + 32 * GFB_FF_ROWS <= (long)g.v3 * t_count) {
+            const Coord xp = decode_site(g, np, t_begin, t_count);
+            const Coord xt = step(g, xp, 3, +1);
+            const unsigned sb = (unsigned)g.v3 * 16u;
+            if (mu < 3) {
+                const char* b = reinterpret_cast<const char*>(uin + link_offset(g, xt, mu));
+#pragma unroll
+                for (int k = 0; k < 9; k++)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(b + (size_t)k * sb), "r"(512 * GFB_FF_ROWS) : "memory");
+            }
+            if (READ_Z) {
+                const char* b = reinterpret_cast<const char*>(zin + mom_offset(g, xp, mu));
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(b + (size_t)k * (sb / 2)), "r"(256 * GFB_FF_ROWS) : "memory");
+            }
+        }
+    }
+#endif
     if (n >= (long)g.v3 * t_count) return;
     const Coord x = decode_site(g, n, t_begin, t_count);
     M3 s = staple_sum(uin, g, x, mu);
@@ -58,10 +88,11 @@ k_force_fused(Geom g, int t_begin, int t_count, const double2* __restrict__ uin,
 
 void launch_force_fused(cudaStream_t st, const Geom& g, int t_begin, int t_count, const double2* uin, double2* uout, const double* zin, double* zout,
                         const FusedArgs& fa) {
-    const int SITES = 32;
-    dim3 block(SITES, 4);
+    const int SITES = 32 * GFB_FF_ROWS;
+    dim3 block(32, 4, GFB_FF_ROWS);
     long nsites = (long)g.v3 * t_count;
     if (nsites <= 0) return;
+    if (launch_rowtile_fused(st, g, t_begin, t_count, uin, uout, zin, zout, fa)) return;
     dim3 grid((unsigned)((nsites + SITES - 1) / SITES));
 #define GFB_LAUNCH_FF(R, W, E) k_force_fused<R, W, E><<<grid, block, 0, st>>>(g, t_begin, t_count, uin, uout, zin, zout, fa.a, fa.b, fa.c)
     if (fa.read_z) {

@@ -41,9 +41,90 @@ __device__ __forceinline__ double block_sum(double v) {
 // U_mu(x) * V_mu(x)^dagger with V_mu the sum of the six plaquette staples
 //   V_mu = sum_{nu != mu} [ U_nu(x) U_mu(x+nu) U_nu(x+mu)^dag + U_nu(x-nu)^dag U_mu(x-nu) U_nu(x-nu+mu) ]
 // (src/autostaples/wilsonloops.jl:468-484, construct_double_staple! src/AbstractGaugefields.jl:2856-2871)
+#ifndef GFB_FF_NOMATH
+#define GFB_FF_NOMATH 0
+#endif
+#ifndef GFB_FF_XOR
+#define GFB_FF_XOR 0
+#endif
+#ifndef GFB_FF_PIPE
+#define GFB_FF_PIPE 0  // 0: compiler-scheduled loads; 1: all three operands of a staple requested up front; 2: next staple prefetched in registers
+#endif
+
+// 128-bit read-only load that the compiler may not sink towards its first use
+__device__ __forceinline__ double2 ldg_pinned(const double2* p) {
+    double2 v;
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ M3 load_link_pinned(const double2* __restrict__ u, const Geom& g, const Coord& c, int mu) {
+    M3 r;
+    const char* b = reinterpret_cast<const char*>(u + link_offset(g, c, mu));
+    const unsigned sb = (unsigned)g.v3 * 16u;
+#pragma unroll
+    for (int k = 0; k < 9; k++) r.e[k] = ldg_pinned(reinterpret_cast<const double2*>(b + (size_t)k * sb));
+    return r;
+}
+
+struct StapleOps {
+    M3 a, b, c;
+};
+// operands of staple j (0..5) of link (x, mu): j>>1 picks nu = (mu+1+(j>>1)) mod 4, j&1 = 0 upper / 1 lower
+__device__ __forceinline__ StapleOps fetch_staple(const double2* __restrict__ u, const Geom& g, const Coord& x, const Coord& xm, int mu, int j) {
+#if GFB_FF_XOR
+    const int nu = mu ^ ((j >> 1) + 1);  // the two links of a plane visit it in the same step: their shared operands hit L1 together
+#else
+    int nu = mu + 1 + (j >> 1);
+    if (nu >= 4) nu -= 4;
+#endif
+    StapleOps o;
+    if ((j & 1) == 0) {
+        const Coord xn = step(g, x, nu, +1);
+        o.a = load_link_pinned(u, g, x, nu);
+        o.b = load_link_pinned(u, g, xn, mu);
+        o.c = load_link_pinned(u, g, xm, nu);
+    } else {
+        const Coord xd = step(g, x, nu, -1);
+        const Coord xdm = step(g, xd, mu, +1);
+        o.a = load_link_pinned(u, g, xd, nu);
+        o.b = load_link_pinned(u, g, xd, mu);
+        o.c = load_link_pinned(u, g, xdm, nu);
+    }
+    return o;
+}
+__device__ __forceinline__ void accumulate_staple(M3& s, const StapleOps& o, int j) {
+#if GFB_FF_NOMATH  // diagnostic build: memory traffic only (profiles/r1_ncu_force_fused.md)
+    m3_add(s, o.a); m3_add(s, o.b); m3_add(s, o.c);
+    return;
+#endif
+    if ((j & 1) == 0) {
+        M3 t = mul_nn(o.a, o.b);
+        mac_nd(s, t, o.c);
+    } else {
+        M3 t = mul_dn(o.a, o.b);
+        mac_nn(s, t, o.c);
+    }
+}
+
 __device__ __forceinline__ M3 staple_sum(const double2* __restrict__ u, const Geom& g, const Coord& x, int mu) {
     M3 s = m3_zero();
     const Coord xm = step(g, x, mu, +1);
+#if GFB_FF_PIPE == 1
+#pragma unroll 1
+    for (int j = 0; j < 6; j++) {
+        const StapleOps o = fetch_staple(u, g, x, xm, mu, j);
+        accumulate_staple(s, o, j);
+    }
+#elif GFB_FF_PIPE == 2
+    StapleOps cur = fetch_staple(u, g, x, xm, mu, 0);
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        StapleOps nxt;
+        if (j < 5) nxt = fetch_staple(u, g, x, xm, mu, j + 1);
+        accumulate_staple(s, cur, j);
+        if (j < 5) cur = nxt;
+    }
+#else
 #pragma unroll kStapleUnroll
     for (int nu = 0; nu < 4; nu++) {
         if (nu == mu) continue;
@@ -65,6 +146,7 @@ __device__ __forceinline__ M3 staple_sum(const double2* __restrict__ u, const Ge
             mac_nn(s, t, a);
         }
     }
+#endif
     return s;
 }
 
