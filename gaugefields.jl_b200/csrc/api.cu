@@ -955,4 +955,214 @@ int gfb_stout_backward(gfb_gauge* d_in, gfb_gauge* d_out, gfb_gauge* in, double 
     return GFB_OK;
 }
 
+// ---- primitive table ------------------------------------------------------------------------------------
+static FieldRef ref_of(const gfb_field* f, size_t i) { return FieldRef{f->d[i], f->slice_planes()}; }
+static Geom geom_of(const gfb_field* f, size_t i) { return make_geom(f->ctx, f->nx, f->ny, f->nz, f->nt, f->ctx->slabs[i].index); }
+static bool same_shape(const gfb_field* a, const gfb_field* b) { return a->ctx == b->ctx && a->nx == b->nx && a->ny == b->ny && a->nz == b->nz && a->nt == b->nt; }
+static void mark_written(gfb_field* f) {
+    f->halo_valid = false;
+    if (f->parent) f->parent->halo_valid = false;
+}
+static bool is_zero(const Shift4& s) { return !s.v[0] && !s.v[1] && !s.v[2] && !s.v[3]; }
+static int read_shift(gfb_ctx* ctx, const int* shift4, Shift4* out) {
+    for (int k = 0; k < 4; k++) out->v[k] = shift4 ? shift4[k] : 0;
+    if (ctx->nslabs_total > 1 && std::abs(out->v[3]) > 1)
+        return fail(ctx, GFB_ERR_ARG, "t-shifts beyond the halo width 1 are not supported on a t-slab decomposition");
+    return GFB_OK;
+}
+// t-halo of ONE field: its 9 planes of the first / last local slice go to the neighbours' halo slots (all 9 both ways)
+static int field_halo(gfb_field* f, const Shift4& s) {
+    gfb_ctx* ctx = f->ctx;
+    const int G = ctx->nslabs_total;
+    if (G == 1 || s.v[3] == 0) return GFB_OK;
+    if (f->halo_valid && !f->parent) return GFB_OK;
+    const size_t v3 = (size_t)f->nx * f->ny * f->nz;
+    const size_t slice = (size_t)f->slice_planes() * v3 * 2, count = 9 * v3 * 2;  // doubles
+    GFB_NCCL(ctx, ncclGroupStart());
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        Slab& sl = ctx->slabs[i];
+        const int prev = (sl.index + G - 1) % G, next = (sl.index + 1) % G;
+        double* base = reinterpret_cast<double*>(f->d[i]);
+        GFB_NCCL(ctx, ncclSend(base, count, ncclDouble, prev, sl.nccl, sl.stream));
+        GFB_NCCL(ctx, ncclSend(base + (size_t)(f->tloc - 1) * slice, count, ncclDouble, next, sl.nccl, sl.stream));
+        GFB_NCCL(ctx, ncclRecv(base + (size_t)f->tloc * slice, count, ncclDouble, next, sl.nccl, sl.stream));
+        GFB_NCCL(ctx, ncclRecv(base + (size_t)(f->tloc + 1) * slice, count, ncclDouble, prev, sl.nccl, sl.stream));
+    }
+    GFB_NCCL(ctx, ncclGroupEnd());
+    f->halo_valid = true;
+    return GFB_OK;
+}
+
+int gfb_field_alloc(gfb_ctx* ctx, int nx, int ny, int nz, int nt, gfb_field** out) {
+    if (!out) return fail(ctx, GFB_ERR_ARG, "out is null");
+    *out = nullptr;
+    GFB_CHECK(check_dims(ctx, nx, ny, nz, nt));
+    gfb_field* f = new gfb_field();
+    f->ctx = ctx; f->nx = nx; f->ny = ny; f->nz = nz; f->nt = nt;
+    f->tloc = nt / ctx->nslabs_total;
+    f->has_halo = ctx->nslabs_total > 1;
+    f->d.assign(ctx->slabs.size(), nullptr);
+    const size_t elems = (size_t)(f->tloc + (f->has_halo ? 2 : 0)) * 9 * (size_t)nx * ny * nz;
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
+        GFB_CUDA(ctx, cudaMalloc(&f->d[i], elems * sizeof(double2)));
+        GFB_CUDA(ctx, cudaMemsetAsync(f->d[i], 0, elems * sizeof(double2), ctx->slabs[i].stream));
+    }
+    *out = f;
+    return GFB_OK;
+}
+int gfb_field_view(gfb_gauge* g, int mu, gfb_field** out) {
+    if (!g || !out) return fail(g ? g->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    if (mu < 0 || mu > 3) return fail(g->ctx, GFB_ERR_ARG, "mu must be in 0..3");
+    gfb_field* f = new gfb_field();
+    f->ctx = g->ctx; f->nx = g->nx; f->ny = g->ny; f->nz = g->nz; f->nt = g->nt; f->tloc = g->tloc;
+    f->has_halo = g->has_halo; f->parent = g; f->mu = mu;
+    f->d.resize(g->d.size());
+    // note: the fused MD / flow passes swap the configuration's buffers; a view is valid until the next such call
+    for (size_t i = 0; i < g->d.size(); i++) f->d[i] = g->d[i] + (size_t)mu * 9 * g->nx * g->ny * g->nz;
+    *out = f;
+    return GFB_OK;
+}
+int gfb_field_free(gfb_field* f) {
+    if (!f) return GFB_OK;
+    if (!f->parent)
+        for (size_t i = 0; i < f->d.size(); i++) { cudaSetDevice(f->ctx->slabs[i].device); cudaFree(f->d[i]); }
+    delete f;
+    return GFB_OK;
+}
+static int field_transfer(gfb_field* f, double* host, bool to_host) {
+    gfb_ctx* ctx = f->ctx;
+    const size_t v3 = (size_t)f->nx * f->ny * f->nz;
+    const size_t bytes = v3 * f->tloc * 9 * sizeof(double2);
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        Slab& s = ctx->slabs[i];
+        GFB_CHECK(ensure_staging(ctx, s, bytes));
+        GFB_CUDA(ctx, cudaSetDevice(s.device));
+        Geom geo = geom_of(f, i);
+        double* h = host + (size_t)geo.t0 * v3 * 18;
+        if (!to_host) GFB_CUDA(ctx, cudaMemcpyAsync(s.d_staging, h, bytes, cudaMemcpyHostToDevice, s.stream));
+        launch_prim_host(s.stream, geo, ref_of(f, i), reinterpret_cast<double2*>(s.d_staging), to_host ? 1 : 0);
+        GFB_CHECK(post_launch(ctx));
+        if (to_host) GFB_CUDA(ctx, cudaMemcpyAsync(h, s.d_staging, bytes, cudaMemcpyDeviceToHost, s.stream));
+    }
+    for (auto& s : ctx->slabs) { GFB_CUDA(ctx, cudaSetDevice(s.device)); GFB_CUDA(ctx, cudaStreamSynchronize(s.stream)); }
+    return GFB_OK;
+}
+int gfb_field_upload(gfb_field* f, const double* host) {
+    if (!f || !host) return fail(f ? f->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    mark_written(f);
+    return field_transfer(f, const_cast<double*>(host), false);
+}
+int gfb_field_download(gfb_field* f, double* host) {
+    if (!f || !host) return fail(f ? f->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    return field_transfer(f, host, true);
+}
+static int field_fill(gfb_field* f, double diag) {
+    if (!f) return fail(nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = f->ctx;
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
+        launch_prim_fill(ctx->slabs[i].stream, geom_of(f, i), ref_of(f, i), diag);
+        GFB_CHECK(post_launch(ctx));
+    }
+    mark_written(f);
+    return GFB_OK;
+}
+int gfb_field_clear(gfb_field* f) { return field_fill(f, 0.0); }
+int gfb_field_unit(gfb_field* f) { return field_fill(f, 1.0); }
+
+static int axpy_impl(gfb_field* c, double2 alpha, gfb_field* a, const int* shift4, int dag, int assign) {
+    if (!c || !a) return fail(c ? c->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = c->ctx;
+    if (!same_shape(c, a)) return fail(ctx, GFB_ERR_ARG, "fields differ in shape");
+    Shift4 s;
+    GFB_CHECK(read_shift(ctx, shift4, &s));
+    if (!is_zero(s) && c->d[0] == a->d[0]) return fail(ctx, GFB_ERR_ARG, "a shifted source must not alias the destination");
+    GFB_CHECK(field_halo(a, s));
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
+        launch_prim_axpy(ctx->slabs[i].stream, geom_of(c, i), ref_of(c, i), alpha, ref_of(a, i), s, dag ? 1 : 0, assign);
+        GFB_CHECK(post_launch(ctx));
+    }
+    mark_written(c);
+    return GFB_OK;
+}
+int gfb_field_copy(gfb_field* dst, gfb_field* src, const int* shift4, int dagger) { return axpy_impl(dst, make_double2(1.0, 0.0), src, shift4, dagger, 1); }
+int gfb_axpy(gfb_field* c, double alpha_re, double alpha_im, gfb_field* a, int dag_a) { return axpy_impl(c, make_double2(alpha_re, alpha_im), a, nullptr, dag_a, 0); }
+
+int gfb_mul(gfb_field* c, gfb_field* a, const int* shift_a4, int dag_a, gfb_field* b, const int* shift_b4, int dag_b, double alpha_re, double alpha_im,
+            double beta_re, double beta_im) {
+    if (!c || !a || !b) return fail(c ? c->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = c->ctx;
+    if (!same_shape(c, a) || !same_shape(c, b)) return fail(ctx, GFB_ERR_ARG, "fields differ in shape");
+    Shift4 sa, sb;
+    GFB_CHECK(read_shift(ctx, shift_a4, &sa));
+    GFB_CHECK(read_shift(ctx, shift_b4, &sb));
+    if ((c->d[0] == a->d[0] && !is_zero(sa)) || (c->d[0] == b->d[0] && !is_zero(sb)))
+        return fail(ctx, GFB_ERR_ARG, "the destination of mul! must not alias a shifted operand");
+    GFB_CHECK(field_halo(a, sa));
+    GFB_CHECK(field_halo(b, sb));
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
+        launch_prim_mul(ctx->slabs[i].stream, geom_of(c, i), ref_of(c, i), ref_of(a, i), sa, dag_a ? 1 : 0, ref_of(b, i), sb, dag_b ? 1 : 0,
+                        make_double2(alpha_re, alpha_im), make_double2(beta_re, beta_im));
+        GFB_CHECK(post_launch(ctx));
+    }
+    mark_written(c);
+    return GFB_OK;
+}
+static int trace_impl(gfb_field* a, gfb_field* b, double* out2) {
+    if (!a || !out2) return fail(a ? a->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = a->ctx;
+    if (b && !same_shape(a, b)) return fail(ctx, GFB_ERR_ARG, "fields differ in shape");
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        Slab& s = ctx->slabs[i];
+        Geom geo = geom_of(a, i);
+        GFB_CHECK(ensure_partial(ctx, s, (size_t)plaquette_blocks(geo) * 2 + 16));
+        GFB_CUDA(ctx, cudaSetDevice(s.device));
+        int nb = 0;
+        launch_prim_trace(s.stream, geo, ref_of(a, i), b ? ref_of(b, i) : ref_of(a, i), b ? 1 : 0, s.d_partial, &nb);
+        launch_final_reduce(s.stream, s.d_partial, nb, s.d_result);
+        launch_final_reduce(s.stream, s.d_partial + nb, nb, s.d_result + 1);
+        GFB_CHECK(post_launch(ctx, 3));
+    }
+    return gather_scalars(ctx, 2, out2);
+}
+int gfb_tr(gfb_field* a, double* out2) { return trace_impl(a, nullptr, out2); }
+int gfb_tr2(gfb_field* a, gfb_field* b, double* out2) {
+    if (!b) return fail(a ? a->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    return trace_impl(a, b, out2);
+}
+static int ta_exp_impl(gfb_field* out, gfb_field* in, int mode, double t) {
+    if (!out || !in) return fail(out ? out->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = out->ctx;
+    if (!same_shape(out, in)) return fail(ctx, GFB_ERR_ARG, "fields differ in shape");
+    if (!std::isfinite(t)) return fail(ctx, GFB_ERR_ARG, "t must be finite");
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
+        launch_prim_ta_exp(ctx->slabs[i].stream, geom_of(out, i), ref_of(out, i), ref_of(in, i), mode, t);
+        GFB_CHECK(post_launch(ctx));
+    }
+    mark_written(out);
+    return GFB_OK;
+}
+int gfb_ta_project(gfb_field* q, gfb_field* m) { return ta_exp_impl(q, m, 0, 1.0); }
+int gfb_exp(gfb_field* e, double t, gfb_field* q) { return ta_exp_impl(e, q, 1, t); }
+static int mom_impl(gfb_field* f, gfb_mom* p, int mu, int mode, double s) {
+    if (!f || !p) return fail(f ? f->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = f->ctx;
+    if (mu < 0 || mu > 3) return fail(ctx, GFB_ERR_ARG, "mu must be in 0..3");
+    if (f->ctx != p->ctx || f->nx != p->nx || f->ny != p->ny || f->nz != p->nz || f->nt != p->nt) return fail(ctx, GFB_ERR_ARG, "fields differ in shape");
+    if (!std::isfinite(s)) return fail(ctx, GFB_ERR_ARG, "the scalar must be finite");
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
+        launch_prim_mom(ctx->slabs[i].stream, geom_of(f, i), ref_of(f, i), p->d[i], mu, mode, s);
+        GFB_CHECK(post_launch(ctx));
+    }
+    if (mode == 1) mark_written(f);
+    return GFB_OK;
+}
+int gfb_ta_coeffs_add(gfb_mom* p, int mu, double factor, gfb_field* m) { return mom_impl(m, p, mu, 0, factor); }
+int gfb_exp_mom(gfb_field* e, double t, gfb_mom* p, int mu) { return mom_impl(e, p, mu, 1, t); }
+
 }  // extern "C"

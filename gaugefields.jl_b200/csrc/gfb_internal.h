@@ -54,7 +54,33 @@ struct gfb_mom {
     size_t elems_per_slab() const { return (size_t)tloc * 32 * (size_t)nx * ny * nz; }
 };
 
+// one 3x3 matrix field (primitive table): either its own buffer (9 planes per slice) or a view of U[mu] (36 planes per slice)
+struct gfb_field {
+    gfb_ctx* ctx = nullptr;
+    int nx = 0, ny = 0, nz = 0, nt = 0, tloc = 0;
+    bool has_halo = false, halo_valid = false;
+    gfb_gauge* parent = nullptr;  // non-null for views
+    int mu = 0;
+    std::vector<double2*> d;      // per local slab: pointer to plane 0 of slice 0 of this field
+    int slice_planes() const { return parent ? 36 : 9; }
+};
+
 namespace gfb {
+
+struct FieldRef {
+    double2* p;
+    int slice_planes;
+};
+struct Shift4 {
+    int v[4];
+};
+void launch_prim_mul(cudaStream_t st, const Geom& g, FieldRef c, FieldRef a, Shift4 sa, int da, FieldRef b, Shift4 sb, int db, double2 alpha, double2 beta);
+void launch_prim_axpy(cudaStream_t st, const Geom& g, FieldRef c, double2 alpha, FieldRef a, Shift4 sa, int da, int assign);
+void launch_prim_fill(cudaStream_t st, const Geom& g, FieldRef c, double diag);
+void launch_prim_trace(cudaStream_t st, const Geom& g, FieldRef a, FieldRef b, int two, double* partial, int* nblocks);
+void launch_prim_ta_exp(cudaStream_t st, const Geom& g, FieldRef out, FieldRef in, int mode, double t);
+void launch_prim_mom(cudaStream_t st, const Geom& g, FieldRef f, double* p, int mu, int mode, double s);
+void launch_prim_host(cudaStream_t st, const Geom& g, FieldRef f, double2* staging, int to_host);
 
 Geom make_geom(const gfb_ctx* ctx, int nx, int ny, int nz, int nt, int slab_global_index);
 

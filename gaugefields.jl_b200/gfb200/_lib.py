@@ -62,6 +62,23 @@ SIGNATURES = {
     "gfb_stout_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_double]),
     "gfb_kick_from_dSdU": (c_int, [c_void_p, c_void_p, c_void_p, c_double]),
     "gfb_wilson_dSdU": (c_int, [c_void_p, c_void_p, c_double]),
+    # primitive table
+    "gfb_field_alloc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, P(c_void_p)]),
+    "gfb_field_view": (c_int, [c_void_p, c_int, P(c_void_p)]),
+    "gfb_field_free": (c_int, [c_void_p]),
+    "gfb_field_upload": (c_int, [c_void_p, c_void_p]),
+    "gfb_field_download": (c_int, [c_void_p, c_void_p]),
+    "gfb_field_clear": (c_int, [c_void_p]),
+    "gfb_field_unit": (c_int, [c_void_p]),
+    "gfb_field_copy": (c_int, [c_void_p, c_void_p, P(c_int), c_int]),
+    "gfb_mul": (c_int, [c_void_p, c_void_p, P(c_int), c_int, c_void_p, P(c_int), c_int, c_double, c_double, c_double, c_double]),
+    "gfb_axpy": (c_int, [c_void_p, c_double, c_double, c_void_p, c_int]),
+    "gfb_tr": (c_int, [c_void_p, P(c_double)]),
+    "gfb_tr2": (c_int, [c_void_p, c_void_p, P(c_double)]),
+    "gfb_ta_project": (c_int, [c_void_p, c_void_p]),
+    "gfb_ta_coeffs_add": (c_int, [c_void_p, c_int, c_double, c_void_p]),
+    "gfb_exp": (c_int, [c_void_p, c_double, c_void_p]),
+    "gfb_exp_mom": (c_int, [c_void_p, c_double, c_void_p, c_int]),
 }
 
 _lib = None

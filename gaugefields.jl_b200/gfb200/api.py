@@ -29,6 +29,8 @@ __all__ = [
     "energy_density", "stout_smearing", "smear", "Philox4x32", "GfbError", "gauge_lattice_size",
     "gauge_num_colors", "gauge_process_grid", "download_configuration", "upload_configuration_",
     "calc_smearedU", "back_prop", "calc_dSdU", "stout_force_", "evaluate_GaugeAction",
+    "MatrixField", "link_field", "shift_U", "clear_U_", "unit_U_", "substitute_U_", "mul_", "add_U_", "tr",
+    "Traceless_antihermitian_", "Traceless_antihermitian_add_", "exptU_",
 ]
 
 
@@ -688,3 +690,164 @@ def stout_force_(P, U, action, smearing, step_size):
     bare = back_prop(dS, smearing, multi, U)
     U.backend.call("gfb_kick_from_dSdU", P._h, U._h, bare._h, -float(step_size) / 3.0)
     return P
+
+
+# ------------------------------------------------------------------------------------------------
+# primitive table: the element-wise operations the reference's generic algorithms are written in
+# (src/4D/mpi_jacc/gaugefields_4D_MPILattice.jl:474-842; semantics SURVEY.md Appendix A)
+# ------------------------------------------------------------------------------------------------
+class _Lazy:
+    """shift_U(A, s) / A' : lazy views (Shifted_/Adjoint_Gaugefields_4D_MPILattice, :647-689)."""
+
+    def __init__(self, field, shift=(0, 0, 0, 0), dagger=False):
+        self.field, self.shift, self.dagger = field, tuple(int(v) for v in shift), bool(dagger)
+
+    def adjoint(self):
+        return _Lazy(self.field, self.shift, not self.dagger)
+
+    @property
+    def H(self):
+        return self.adjoint()
+
+
+def _unlazy(a):
+    if isinstance(a, _Lazy):
+        return a.field, a.shift, a.dagger
+    return a, (0, 0, 0, 0), False
+
+
+def _shift_arg(shift):
+    return (ctypes.c_int * 4)(*shift) if any(shift) else None
+
+
+class MatrixField:
+    """One Gaugefields_4D: a 3x3 complex matrix per site (a link direction U[mu] or a temporary from similar(U[1]))."""
+
+    def __init__(self, backend, lattice, handle=None, owner=None):
+        self.backend, self.lattice = backend, tuple(int(v) for v in lattice)
+        self.NC, self.NDW = 3, 1
+        self.NX, self.NY, self.NZ, self.NT = self.lattice
+        self.NV = int(np.prod(self.lattice))
+        self._owner = owner  # keeps the viewed configuration alive
+        self._h = handle if handle is not None else ctypes.c_void_p()
+        if handle is None:
+            backend.call("gfb_field_alloc", backend._ctx, *self.lattice, ctypes.byref(self._h))
+
+    def __del__(self):
+        try:
+            if self._h and self.backend._ctx:
+                self.backend.lib.gfb_field_free(self._h)
+        except Exception:
+            pass
+
+    def similar(self):
+        return MatrixField(self.backend, self.lattice)
+
+    def host_shape(self):
+        nx, ny, nz, nt = self.lattice
+        return (nt, nz, ny, nx, 3, 3)
+
+    def upload(self, host):
+        host = np.ascontiguousarray(host, dtype=np.complex128)
+        if host.shape != self.host_shape():
+            raise ValueError("expected shape %s, got %s" % (self.host_shape(), host.shape))
+        self.backend.call("gfb_field_upload", self._h, ctypes.c_void_p(host.ctypes.data))
+        return self
+
+    def to_host(self):
+        out = np.zeros(self.host_shape(), dtype=np.complex128)
+        self.backend.call("gfb_field_download", self._h, ctypes.c_void_p(out.ctypes.data))
+        return out
+
+    def adjoint(self):
+        return _Lazy(self, dagger=True)
+
+    @property
+    def H(self):
+        return self.adjoint()
+
+
+def link_field(U, mu):
+    """U[mu] as a MatrixField aliasing the configuration (valid until the next fused MD/flow call swaps its buffers)."""
+    h = ctypes.c_void_p()
+    U.backend.call("gfb_field_view", U._h, int(mu), ctypes.byref(h))
+    return MatrixField(U.backend, U.lattice, handle=h, owner=U)
+
+
+def shift_U(A, shift):
+    """shift_U(A, nu) / shift_U(A, (s1,s2,s3,s4)): B(x) = A(x + s), periodic (:647-675).  Integer nu is 1-based like Julia's,
+    negative for the backward direction."""
+    f, s0, dag = _unlazy(A)
+    if isinstance(shift, int):
+        v = [0, 0, 0, 0]
+        v[abs(shift) - 1] = 1 if shift > 0 else -1
+        shift = v
+    return _Lazy(f, tuple(a + b for a, b in zip(s0, shift)), dag)
+
+
+def clear_U_(A):
+    A.backend.call("gfb_field_clear", A._h)
+    return A
+
+
+def unit_U_(A):
+    A.backend.call("gfb_field_unit", A._h)
+    return A
+
+
+def substitute_U_(A, B):
+    """substitute_U!(A, B) with B plain / shifted / adjoint (:509-575)."""
+    f, s, dag = _unlazy(B)
+    A.backend.call("gfb_field_copy", A._h, f._h, _shift_arg(s), int(dag))
+    return A
+
+
+def mul_(C, A, B, alpha=1.0, beta=0.0):
+    """mul!(C, A, B[, alpha, beta]): C = alpha*A*B + beta*C with lazy shifted / adjoint operands (AbstractGaugefields.jl:2082-2105)."""
+    fa, sa, da = _unlazy(A)
+    fb, sb, db = _unlazy(B)
+    alpha, beta = complex(alpha), complex(beta)
+    C.backend.call("gfb_mul", C._h, fa._h, _shift_arg(sa), int(da), fb._h, _shift_arg(sb), int(db), alpha.real, alpha.imag, beta.real, beta.imag)
+    return C
+
+
+def add_U_(C, *args):
+    """add_U!(C, A) / add_U!(C, alpha, A), A plain or adjoint (:739-772)."""
+    alpha, A = (1.0, args[0]) if len(args) == 1 else args
+    f, s, dag = _unlazy(A)
+    if any(s):
+        raise ValueError("add_U! takes plain or adjoint operands")
+    alpha = complex(alpha)
+    C.backend.call("gfb_axpy", C._h, alpha.real, alpha.imag, f._h, int(dag))
+    return C
+
+
+def tr(A, B=None):
+    """tr(A) = sum_x tr A(x);  tr(A, B) = sum_x tr(A(x) B(x)) (:721-728)."""
+    out = (ctypes.c_double * 2)()
+    if B is None:
+        A.backend.call("gfb_tr", A._h, out)
+    else:
+        A.backend.call("gfb_tr2", A._h, B._h, out)
+    return complex(out[0], out[1])
+
+
+def Traceless_antihermitian_(Q, M):
+    """Traceless_antihermitian!(Q, M), matrix -> matrix (:774-781)."""
+    Q.backend.call("gfb_ta_project", Q._h, M._h)
+    return Q
+
+
+def Traceless_antihermitian_add_(P, mu, factor, M):
+    """Traceless_antihermitian_add!(P[mu], factor, M): 8 coefficients (TA_gaugefields_4D_MPILattice.jl:263-283)."""
+    M.backend.call("gfb_ta_coeffs_add", P._h, int(mu), float(factor), M._h)
+    return P
+
+
+def exptU_(E, t, Q, mu=None):
+    """exptU!(E, t, Q): Q a matrix field (E = exp(t TA(Q)), :798-808) or the momenta with a direction (TA_...:196-210)."""
+    if isinstance(Q, Momenta):
+        E.backend.call("gfb_exp_mom", E._h, float(t), Q._h, int(mu))
+    else:
+        E.backend.call("gfb_exp", E._h, float(t), Q._h)
+    return E

@@ -285,3 +285,77 @@ function layer_pullback!(δ_prev::AbstractVector{<:Gaugefields_4D_B200}, δ_curr
         _b200_handle(δ_prev).ptr, _b200_handle(δ_current).ptr, h.ptr, Float64(real(layer.ρs[1]))), h.ctx.ptr)
     return
 end
+
+
+# ---- primitive table (keeps the generic, un-fused algorithms of Gaugefields.jl working on this backend) --------------
+# A single link field / temporary is a `gfb_field`; `U[mu]` of a configuration is a view (gfb_field_view).  Lazy
+# shift / adjoint views mirror Shifted_/Adjoint_Gaugefields_4D_MPILattice (gaugefields_4D_MPILattice.jl:647-689).
+mutable struct B200FieldHandle
+    ptr::Ptr{Cvoid}
+    ctx::B200Context
+    owner::Any
+end
+struct B200Lazy
+    field::B200FieldHandle
+    shift::NTuple{4,Cint}
+    dagger::Bool
+end
+_lazy(f::B200FieldHandle) = B200Lazy(f, (Cint(0), Cint(0), Cint(0), Cint(0)), false)
+_lazy(l::B200Lazy) = l
+Base.adjoint(f::B200FieldHandle) = B200Lazy(f, (Cint(0), Cint(0), Cint(0), Cint(0)), true)
+Base.adjoint(l::B200Lazy) = B200Lazy(l.field, l.shift, !l.dagger)
+shift_U(f::Union{B200FieldHandle,B200Lazy}, s::NTuple{4,<:Integer}) =
+    (l = _lazy(f); B200Lazy(l.field, Cint.(l.shift .+ s), l.dagger))
+_shiftptr(s) = all(iszero, s) ? C_NULL : pointer(collect(s))
+
+function b200_similar(f::B200FieldHandle, dims::NTuple{4,Int})
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    _gfb_check(ccall((:gfb_field_alloc, LIBGFB200), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Ref{Ptr{Cvoid}}), f.ctx.ptr, dims..., out), f.ctx.ptr)
+    h = B200FieldHandle(out[], f.ctx, nothing)
+    finalizer(x -> ccall((:gfb_field_free, LIBGFB200), Cint, (Ptr{Cvoid},), x.ptr), h)
+    return h
+end
+function b200_link(u::Gaugefields_4D_B200)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    _gfb_check(ccall((:gfb_field_view, LIBGFB200), Cint, (Ptr{Cvoid}, Cint, Ref{Ptr{Cvoid}}), u.handle.ptr, u.mu - 1, out), u.handle.ctx.ptr)
+    h = B200FieldHandle(out[], u.handle.ctx, u.handle)
+    finalizer(x -> ccall((:gfb_field_free, LIBGFB200), Cint, (Ptr{Cvoid},), x.ptr), h)
+    return h
+end
+# mul!(C, A, B, alpha, beta)  (src/AbstractGaugefields.jl:2082-2105)
+function LinearAlgebra.mul!(C::B200FieldHandle, A, B, α::Number=1, β::Number=0)
+    a, b = _lazy(A), _lazy(B)
+    sa, sb = collect(a.shift), collect(b.shift)
+    GC.@preserve sa sb _gfb_check(ccall((:gfb_mul, LIBGFB200), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cint}, Cint, Ptr{Cvoid}, Ptr{Cint}, Cint, Cdouble, Cdouble, Cdouble, Cdouble),
+        C.ptr, a.field.ptr, sa, a.dagger, b.field.ptr, sb, b.dagger, real(α), imag(α), real(β), imag(β)), C.ctx.ptr)
+    return C
+end
+add_U!(C::B200FieldHandle, α::Number, A) = (a = _lazy(A);
+    _gfb_check(ccall((:gfb_axpy, LIBGFB200), Cint, (Ptr{Cvoid}, Cdouble, Cdouble, Ptr{Cvoid}, Cint), C.ptr, real(α), imag(α), a.field.ptr, a.dagger), C.ctx.ptr); C)
+add_U!(C::B200FieldHandle, A) = add_U!(C, 1.0, A)
+clear_U!(C::B200FieldHandle) = (_gfb_check(ccall((:gfb_field_clear, LIBGFB200), Cint, (Ptr{Cvoid},), C.ptr), C.ctx.ptr); C)
+unit_U!(C::B200FieldHandle) = (_gfb_check(ccall((:gfb_field_unit, LIBGFB200), Cint, (Ptr{Cvoid},), C.ptr), C.ctx.ptr); C)
+function substitute_U!(A::B200FieldHandle, B)
+    b = _lazy(B); s = collect(b.shift)
+    GC.@preserve s _gfb_check(ccall((:gfb_field_copy, LIBGFB200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cint}, Cint), A.ptr, b.field.ptr, s, b.dagger), A.ctx.ptr)
+    return A
+end
+function LinearAlgebra.tr(A::B200FieldHandle)
+    out = zeros(Cdouble, 2)
+    _gfb_check(ccall((:gfb_tr, LIBGFB200), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), A.ptr, out), A.ctx.ptr)
+    return complex(out[1], out[2])
+end
+function LinearAlgebra.tr(A::B200FieldHandle, B::B200FieldHandle)
+    out = zeros(Cdouble, 2)
+    _gfb_check(ccall((:gfb_tr2, LIBGFB200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cdouble}), A.ptr, B.ptr, out), A.ctx.ptr)
+    return complex(out[1], out[2])
+end
+Traceless_antihermitian!(Q::B200FieldHandle, M::B200FieldHandle) =
+    (_gfb_check(ccall((:gfb_ta_project, LIBGFB200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), Q.ptr, M.ptr), Q.ctx.ptr); Q)
+Traceless_antihermitian_add!(P::TA_Gaugefields_4D_B200, factor, M::B200FieldHandle) =
+    (_gfb_check(ccall((:gfb_ta_coeffs_add, LIBGFB200), Cint, (Ptr{Cvoid}, Cint, Cdouble, Ptr{Cvoid}), P.handle.ptr, P.mu - 1, Float64(factor), M.ptr), M.ctx.ptr); P)
+exptU!(E::B200FieldHandle, t, Q::B200FieldHandle, temps=nothing) =
+    (_gfb_check(ccall((:gfb_exp, LIBGFB200), Cint, (Ptr{Cvoid}, Cdouble, Ptr{Cvoid}), E.ptr, Float64(t), Q.ptr), E.ctx.ptr); E)
+exptU!(E::B200FieldHandle, t, P::TA_Gaugefields_4D_B200, temps=nothing) =
+    (_gfb_check(ccall((:gfb_exp_mom, LIBGFB200), Cint, (Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Cint), E.ptr, Float64(t), P.handle.ptr, P.mu - 1), E.ctx.ptr); E)

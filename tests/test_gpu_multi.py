@@ -90,6 +90,40 @@ def test_two_slabs_match_oracle(backend2, oracle):
     assert np.abs(F.to_host() - Fw).max() / np.abs(Fw).max() < 1e-12
 
 
+def test_primitive_table_across_slabs(backend2, oracle):
+    """shifted / adjoint mul! and tr with t-shifts that cross the slab faces (field-level halo exchange)."""
+    import gfb200 as g
+
+    dims = DIMS
+    Uh = oracle.hot_start_philox(dims, 21)
+    U = g.gauge_configuration(dims, backend=backend2).upload(Uh)
+    L = [g.link_field(U, mu) for mu in range(4)]
+    t1, t2, V = L[0].similar(), L[0].similar(), L[0].similar()
+    plaq = 0.0
+    for mu in range(4):
+        g.clear_U_(V)
+        for nu in range(4):
+            if nu == mu:
+                continue
+            g.mul_(t1, L[nu], g.shift_U(L[mu], nu + 1))
+            g.mul_(V, t1, g.shift_U(L[nu], mu + 1).H, 1.0, 1.0)
+            # lower staple too, so backward t-shifts of views and temporaries are exercised
+            g.mul_(t1, g.shift_U(L[nu], -(nu + 1)).H, g.shift_U(L[mu], -(nu + 1)))
+            sh = [0, 0, 0, 0]
+            sh[mu] += 1
+            sh[nu] -= 1
+            g.mul_(V, t1, g.shift_U(L[nu], sh), 1.0, 1.0)
+        g.mul_(t2, L[mu], V.H)
+        plaq += g.tr(t2)
+    want = oracle.plaquette_sum(Uh, dims)
+    assert abs(plaq.real * 0.25 - want) < 1e-12 * abs(want) + 1e-12  # upper + lower staples count every plaquette four times
+    B = t1.similar()
+    g.substitute_U_(B, g.shift_U(t2, (0, 0, 0, 1)))
+    assert np.array_equal(B.to_host(), np.roll(t2.to_host(), -1, axis=0))
+    with pytest.raises(ValueError):
+        g.substitute_U_(B, g.shift_U(t2, (0, 0, 0, 2)))  # wider than the halo
+
+
 def test_random_fields_are_decomposition_independent(backend2, backend):
     """hot start and Gaussian momenta are keyed by the GLOBAL site: bit-identical on 1 and 2 slabs
     (test/MPIJACCtest/random_fields_site_rng.jl:148-172)."""
