@@ -111,6 +111,9 @@ struct FusedArgs {
 };
 void launch_force_fused(cudaStream_t st, const Geom& g, int t_begin, int t_count, const double2* uin, double2* uout, const double* zin, double* zout,
                         const FusedArgs& fa);
+// persistent t-marching shared-memory variant of launch_force_fused (tmarch.cu); false = launch not covered, nothing launched
+bool launch_tmarch_fused(cudaStream_t st, const Geom& g, int t_begin, int t_count, const double2* uin, double2* uout, const double* zin, double* zout,
+                         const FusedArgs& fa);
 // persistent TMA row-tile variant of launch_force_fused (rowtile.cu); false = geometry not covered, nothing launched
 bool launch_rowtile_fused(cudaStream_t st, const Geom& g, int t_begin, int t_count, const double2* uin, double2* uout, const double* zin, double* zout,
                           const FusedArgs& fa);

@@ -92,6 +92,7 @@ void launch_force_fused(cudaStream_t st, const Geom& g, int t_begin, int t_count
     dim3 block(32, 4, GFB_FF_ROWS);
     long nsites = (long)g.v3 * t_count;
     if (nsites <= 0) return;
+    if (launch_tmarch_fused(st, g, t_begin, t_count, uin, uout, zin, zout, fa)) return;
     if (launch_rowtile_fused(st, g, t_begin, t_count, uin, uout, zin, zout, fa)) return;
     dim3 grid((unsigned)((nsites + SITES - 1) / SITES));
 #define GFB_LAUNCH_FF(R, W, E) k_force_fused<R, W, E><<<grid, block, 0, st>>>(g, t_begin, t_count, uin, uout, zin, zout, fa.a, fa.b, fa.c)
