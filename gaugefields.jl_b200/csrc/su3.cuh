@@ -237,32 +237,6 @@ __device__ __forceinline__ M3 ta_from_coeffs(const double* c) {
     return q;
 }
 
-static __constant__ double c_inv_factorial[24] = {
-    1.0,
-    1.0,
-    1.0 / 2.0,
-    1.0 / 6.0,
-    1.0 / 24.0,
-    1.0 / 120.0,
-    1.0 / 720.0,
-    1.0 / 5040.0,
-    1.0 / 40320.0,
-    1.0 / 362880.0,
-    1.0 / 3628800.0,
-    1.0 / 39916800.0,
-    1.0 / 479001600.0,
-    1.0 / 6227020800.0,
-    1.0 / 87178291200.0,
-    1.0 / 1307674368000.0,
-    1.0 / 20922789888000.0,
-    1.0 / 355687428096000.0,
-    1.0 / 6402373705728000.0,
-    1.0 / 121645100408832000.0,
-    1.0 / 2432902008176640000.0,
-    1.0 / 51090942171709440000.0,
-    1.0 / 1124000727777607680000.0,
-    1.0 / 25852016738884976640000.0,
-};
 
 // Hermitian traceless Q in compact form: 3 real diagonal + 3 complex upper entries.
 struct H3 {
@@ -285,24 +259,39 @@ __device__ __forceinline__ H3 h3_from_coeffs(const double* c, double t) {
 // f0,f1,f2 with exp(iQ) = f0 + f1 Q + f2 Q^2 for Hermitian traceless Q with
 // c0 = det Q, c1 = tr(Q^2)/2 (Q^3 = c1 Q + c0).  Horner evaluation of the Taylor series
 // reduced with the Cayley-Hamilton relation; valid for c1 <= 0.75 (|eigenvalues| <= 1).
-__device__ __forceinline__ void ch_coefficients(double c0, double c1, double2& f0, double2& f1, double2& f2) {
-    const int N = (c1 <= 0.046875) ? 14 : 21;
-    // a_n = i^n / n!
-    double2 p0, p1 = make_double2(0.0, 0.0), p2 = make_double2(0.0, 0.0);
-    {
-        double a = c_inv_factorial[N];
-        int m = N & 3;
-        p0 = (m == 0) ? make_double2(a, 0.0) : (m == 1) ? make_double2(0.0, a) : (m == 2) ? make_double2(-a, 0.0) : make_double2(0.0, -a);
-    }
-    for (int n = N - 1; n >= 0; n--) {
-        double a = c_inv_factorial[n];
-        int m = n & 3;
-        double2 an = (m == 0) ? make_double2(a, 0.0) : (m == 1) ? make_double2(0.0, a) : (m == 2) ? make_double2(-a, 0.0) : make_double2(0.0, -a);
-        double2 n0 = make_double2(fma(c0, p2.x, an.x), fma(c0, p2.y, an.y));
-        double2 n1 = make_double2(fma(c1, p2.x, p0.x), fma(c1, p2.y, p0.y));
-        p2 = p1; p1 = n1; p0 = n0;
-    }
+// Fully unrolled with immediate coefficients: the recursion is linear with REAL coefficients (c0, c1), so the real
+// parts (driven by the even a_n = i^n/n!) and the imaginary parts (odd n) are two independent real recursions of
+// 2 FMA per term each.  (The first version looped with a constant-memory table and per-term selects: ~45 instructions
+// per term and the top stall of the t-marching kernel -- profiles/r1_tmarch.md.)
+template <int n>
+struct InvFactorial {
+    static constexpr double v = InvFactorial<n - 1>::v / (double)n;
+};
+template <>
+struct InvFactorial<0> {
+    static constexpr double v = 1.0;
+};
+// one Horner term:  p <- a_n + Q p  reduced mod Q^3 = c1 Q + c0:  (p0, p1, p2) <- (a_n + c0 p2, p0 + c1 p2, p1)
+template <int n>
+__device__ __forceinline__ void ch_terms(double c0, double c1, double2& p0, double2& p1, double2& p2) {
+    constexpr double a = ((n & 2) ? -1.0 : 1.0) * InvFactorial<n>::v;  // a_n = i^n/n!: real for even n, imaginary for odd n
+    double2 n0, n1;
+    if ((n & 1) == 0) { n0.x = fma(c0, p2.x, a); n0.y = c0 * p2.y; }
+    else { n0.x = c0 * p2.x; n0.y = fma(c0, p2.y, a); }
+    n1.x = fma(c1, p2.x, p0.x);
+    n1.y = fma(c1, p2.y, p0.y);
+    p2 = p1; p1 = n1; p0 = n0;
+    if constexpr (n > 0) ch_terms<n - 1>(c0, c1, p0, p1, p2);
+}
+template <int N>
+__device__ __forceinline__ void ch_coefficients_n(double c0, double c1, double2& f0, double2& f1, double2& f2) {
+    double2 p0 = make_double2(0.0, 0.0), p1 = make_double2(0.0, 0.0), p2 = make_double2(0.0, 0.0);
+    ch_terms<N>(c0, c1, p0, p1, p2);
     f0 = p0; f1 = p1; f2 = p2;
+}
+__device__ __forceinline__ void ch_coefficients(double c0, double c1, double2& f0, double2& f1, double2& f2) {
+    if (c1 <= 0.046875) ch_coefficients_n<14>(c0, c1, f0, f1, f2);
+    else ch_coefficients_n<21>(c0, c1, f0, f1, f2);
 }
 
 // E = exp(i Q).  Arguments with spectral radius > 1 are scaled by 2^-s and squared back.

@@ -5,10 +5,12 @@
 // Why (profiles/r1_ncu_force_fused.md): k_force_fused requests 19 link matrices per link through L1 (10.9 KB/site), 6.0 KB/site of
 // which come from L2 at the ~7 TB/s the L2->SM path delivers at 16 warps/SM; neither DRAM nor the FP64 pipe is the limit.
 // Here a CTA owns a spatial tile of 8x4x2 sites and marches along t.  Every link matrix the six-staple stencil of a slice needs is
-// copied into shared memory ONCE per tile and slice with 16-byte cp.async (LDGSTS, L1-bypassing), one whole slice ahead of its
-// use, so L2->SM traffic drops to 2.64 matrix loads per link (1.5 KB/site) and every operand is a fixed-latency LDS.128.
+// copied into shared memory ONCE per tile and slice by TMA tensor copies (31 boxes per slice, one cp.async.bulk.tensor.4d each,
+// issued by the lanes of warp 0, completion on mbarriers), one whole slice ahead of its use, so L2->SM traffic drops to 2.64
+// matrix loads per link (1.5 KB/site) and every operand is a fixed-latency LDS.128.  (The first version copied with per-thread
+// 16-byte cp.async: issuing 27 LDGSTS per thread and slice cost 24 % of the warp time -- profiles/r1_tmarch.md.)
 // The backward-t staple is carried in registers from the previous slice by the thread that owns the link, so slice t-1 is never
-// resident (tmarch_geom.h has the exact residency sets and the ring layout: 230400 bytes of shared memory, one CTA per SM).
+// resident (tmarch_geom.h has the exact residency sets and the ring layout: 231 KB of shared memory, one CTA per SM).
 //
 // FP64 work: links are SU(3), so every staple A B C is formed from the first two rows of A only (2 x 72 FMA) and its third row
 // is reconstructed as conj(row0 x row1) folded into the accumulation (24 FMA + 12 adds): 180 instead of 216 FP64 instructions per
@@ -16,15 +18,19 @@
 //
 // One thread per (site, mu); a warp holds 32 sites of one direction (mu is a template parameter of the per-warp body, so every
 // operand's ring and part are compile-time and its byte offset is one of 19 per-thread registers computed once per CTA).
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
+
 #include <cstdint>
 #include <cstdlib>
+#include <mutex>
+#include <unordered_map>
 
 #include "gfb_internal.h"
 #include "stencil.cuh"
 #include "tmarch_geom.h"
 
 #ifndef GFB_TM_DEBUG
-#define GFB_TM_DEBUG 0  // 1: no staple arithmetic (copies + operand reads only); 2: no global->shared copies (arithmetic on stale smem)
+#define GFB_TM_DEBUG 0  // 1: no staple arithmetic (copies + operand reads only); 2: no global->shared copies (barriers only; arithmetic on stale smem)
 #endif
 
 namespace gfb {
@@ -42,45 +48,70 @@ struct R2 {
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
-#if GFB_TM_DEBUG != 2
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+struct TmMaps {
+    CUtensorMap m[tm::NSHAPE];  // one per box shape: tensor = [plane][z][y][2*x doubles], box = 9 planes x ez x ey x 2*ex
+};
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+#if GFB_TM_DEBUG == 2
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+#else
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 #endif
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared 4-D tensor copy (TMA), completion counted in bytes on `bar`
+__device__ __forceinline__ void tma_load_4d(unsigned dst_smem, const CUtensorMap* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
+#if GFB_TM_DEBUG != 2
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst_smem),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+                 : "memory");
+#endif
+}
 
-__device__ __forceinline__ M3 lds_m3(const unsigned char* p) {
+// operand in shared memory: element k at p + k*stride (box-dense [k][pos] layout, tmarch_geom.h)
+struct SmOp {
+    const unsigned char* p;
+    unsigned stride;
+};
+__device__ __forceinline__ double2 lds_el(const SmOp& o, int k) { return *reinterpret_cast<const double2*>(o.p + k * o.stride); }
+__device__ __forceinline__ M3 lds_m3(const SmOp& o) {
     M3 r;
-    const double2* q = reinterpret_cast<const double2*>(p);
 #pragma unroll
-    for (int k = 0; k < 9; k++) r.e[k] = q[k];
+    for (int k = 0; k < 9; k++) r.e[k] = lds_el(o, k);
     return r;
 }
-__device__ __forceinline__ R2 lds_rows01(const unsigned char* p) {
+__device__ __forceinline__ R2 lds_rows01(const SmOp& o) {
     R2 r;
-    const double2* q = reinterpret_cast<const double2*>(p);
 #pragma unroll
-    for (int k = 0; k < 6; k++) r.e[k] = q[k];
+    for (int k = 0; k < 6; k++) r.e[k] = lds_el(o, k);
     return r;
 }
 // rows 0,1 of A^dagger: (A^dag)[i][j] = conj(A[j][i])
-__device__ __forceinline__ R2 lds_dag_rows01(const unsigned char* p) {
+__device__ __forceinline__ R2 lds_dag_rows01(const SmOp& o) {
     R2 r;
-    const double2* q = reinterpret_cast<const double2*>(p);
 #pragma unroll
     for (int i = 0; i < 2; i++)
 #pragma unroll
         for (int j = 0; j < 3; j++) {
-            const double2 v = q[3 * j + i];
+            const double2 v = lds_el(o, 3 * j + i);
             r.e[3 * i + j] = make_double2(v.x, -v.y);
         }
-    return r;
-}
-__device__ __forceinline__ R2 rows01(const M3& a) {
-    R2 r;
-#pragma unroll
-    for (int k = 0; k < 6; k++) r.e[k] = a.e[k];
     return r;
 }
 __device__ __forceinline__ R2 rows01_dag(const M3& a) {
@@ -146,29 +177,65 @@ __device__ __forceinline__ M3 complete_su3(const R2& r) {
 
 __device__ __forceinline__ int wrap(int c, int n) { return c < 0 ? c + n : (c >= n ? c - n : c); }
 
-// The whole persistent loop of one link-thread with direction MU.
-template <int MU, bool READ_Z, bool WRITE_Z, bool DO_EXP>
-__device__ __forceinline__ void tm_run(const Geom& g, const TmPlan& pl, const double2* __restrict__ uin, double2* __restrict__ uout,
-                                       const double* __restrict__ zin, double* __restrict__ zout, double a, double b, double c,
-                                       unsigned char* smem, const tm::Box* boxes) {
+// The whole persistent loop of one link-thread.  mu is warp-uniform but NOT a template parameter: all eight warps run the same
+// instructions (a per-direction instantiation made the straight-line staple code four times larger than the instruction
+// cache could hold: "no instruction" was the top stall of the first version, profiles/r1_tmarch.md).
+template <bool READ_Z, bool WRITE_Z, bool DO_EXP>
+__device__ __forceinline__ void tm_run(const int MU, const TmMaps& maps, const Geom& g, const TmPlan& pl, const double2* __restrict__ uin,
+                                       double2* __restrict__ uout, const double* __restrict__ zin, double* __restrict__ zout, double a, double b,
+                                       double c, unsigned char* smem, uint64_t* bars, const tm::Box* boxes) {
     const int tid = threadIdx.x;
     const int sidx = tid & (tm::SITES - 1);
     const int sx = sidx & (tm::BX - 1), sy = (sidx / tm::BX) & (tm::BY - 1), sz = sidx / (tm::BX * tm::BY);
     unsigned char* const sS = smem;
     unsigned char* const sR = smem + tm::S_RING * tm::S_BYTES;
 
-    // ---- consumer side: operand offsets (tile independent)
+    // ---- consumer side: operand descriptors (tile independent): tm::lookup() bits 0-24, ring code in bits 28-29
+    //      (0: S part of slice t, 1: R part of slice t, 2: S part of slice t+1)
     tm::Operands op;
     tm::make_operands(boxes, sx, sy, sz, MU, &op);
+    const int carry_j = (MU < 3) ? 2 - MU : -1;  // the iteration with nu = t of a spatial link
+    {
+        auto cen = [](int d) { return (d & 0xFFFFFF) | (((d >> 24) & 1) << 28); };
+        auto nxt = [](int d) { return (d & 0xFFFFFF) | (2 << 28); };
+        const int own = cen(op.own);
+#pragma unroll
+        for (int jj = 0; jj < 3; jj++) {
+            const int nu = (MU + 1 + jj) & 3;
+            const int a0 = cen(op.up[jj][0]);
+            const int b0 = (MU < 3 && nu == 3) ? nxt(op.up[jj][1]) : cen(op.up[jj][1]);
+            const int c0 = (MU == 3) ? nxt(op.up[jj][2]) : cen(op.up[jj][2]);
+            int a1, b1, c1;
+            if (jj == carry_j) {
+                // next slice's backward-t staple  U_t(x)^dag U_mu(x) U_t(x+mu): same shape as a lower staple, operands from slice t
+                a1 = a0; b1 = own; c1 = c0;
+            } else {
+                a1 = cen(op.dn[jj][0]);
+                b1 = cen(op.dn[jj][1]);
+                c1 = (MU == 3) ? nxt(op.dn[jj][2]) : cen(op.dn[jj][2]);
+            }
+            op.up[jj][0] = a0; op.up[jj][1] = b0; op.up[jj][2] = c0;
+            op.dn[jj][0] = a1; op.dn[jj][1] = b1; op.dn[jj][2] = c1;
+        }
+        op.own = own;
+    }
 
-    // ---- producer side: this thread copies S slot tid and R slots tid, tid+256 of every slice
-    int plam[3], px[3], py[3], pz[3];
-    bool pvalid[3];
-    pvalid[0] = tm::slot_to_pos(boxes, 0, tid, &plam[0], &px[0], &py[0], &pz[0]);
-    pvalid[1] = tm::slot_to_pos(boxes, 1, tid, &plam[1], &px[1], &py[1], &pz[1]);
-    pvalid[2] = tm::slot_to_pos(boxes, 1, tid + tm::NTHREADS, &plam[2], &px[2], &py[2], &pz[2]);
-    const unsigned sb = (unsigned)g.v3 * 16u;          // bytes between element planes
-    const size_t slice_bytes = (size_t)36 * sb;        // bytes of one time-slice of links
+    // ---- producer side: lane b of warp 0 owns box b (31 boxes per slice)
+    const bool is_producer = tid < tm::NBOX;
+    int bx_o[3] = {0, 0, 0}, b_lam = 0, b_isr = 0, b_base = 0, b_shape = 0;
+    if (is_producer) {
+        const tm::Box bb = boxes[tid];
+        bx_o[0] = bb.o[0]; bx_o[1] = bb.o[1]; bx_o[2] = bb.o[2];
+        b_lam = bb.lam; b_isr = bb.is_r; b_base = bb.base;
+        b_shape = tm::shape_index(bb.e[0], bb.e[1], bb.e[2]);
+    }
+    uint64_t* const barS = bars;                 // [S_RING]
+    uint64_t* const barR = bars + tm::S_RING;    // [R_RING]
+    unsigned phases = 0;                         // bit s: parity of the next completion of barrier s (uniform over the CTA)
+    auto wait_bar = [&](int s) {
+        mbar_wait(bars + s, (phases >> s) & 1u);
+        phases ^= 1u << s;
+    };
 
     const long nitems = (long)pl.ntiles * pl.nseg;
     for (long item = blockIdx.x; item < nitems; item += gridDim.x) {
@@ -180,31 +247,24 @@ __device__ __forceinline__ void tm_run(const Geom& g, const TmPlan& pl, const do
         const int tb = pl.t_begin + seg * pl.seg_len;
         const int len = min(pl.seg_len, pl.t_begin + pl.t_count - tb);
 
-        unsigned psrc[3];
-#pragma unroll
-        for (int q = 0; q < 3; q++) {
-            const int s3 = wrap(x0 + px[q], g.nx) + g.nx * (wrap(y0 + py[q], g.ny) + g.ny * wrap(z0 + pz[q], g.nz));
-            psrc[q] = pvalid[q] ? ((unsigned)(plam[q] * 9) * (unsigned)g.v3 + (unsigned)s3) * 16u : 0u;
-        }
-        auto copy_mat = [&](int q, int tslot, unsigned char* dst_part, int slot) {
-            if (!pvalid[q]) return;
-            const char* src = reinterpret_cast<const char*>(uin) + (size_t)tslot * slice_bytes + psrc[q];
-            const unsigned dst = smem_u32(dst_part + slot * tm::MAT_BYTES);
-#pragma unroll
-            for (int k = 0; k < 9; k++) cp_async16(dst + 16 * k, src + (size_t)k * sb);
-        };
-        auto copy_S = [&](int tslot, int ring) { copy_mat(0, tslot, sS + ring * tm::S_BYTES, tid); };
-        auto copy_R = [&](int tslot, int ring) {
-            copy_mat(1, tslot, sR + ring * tm::R_BYTES, tid);
-            copy_mat(2, tslot, sR + ring * tm::R_BYTES, tid + tm::NTHREADS);
+        const int cx = 2 * wrap(x0 + bx_o[0], g.nx), cy = wrap(y0 + bx_o[1], g.ny), cz = wrap(z0 + bx_o[2], g.nz);
+        // one part (all its boxes) of the slice in storage slot `tslot` into ring buffer `ring`; warp 0 only
+        auto copy_part = [&](int is_r, int tslot, int ring) {
+            if (tid >= 32) return;
+            uint64_t* const bar = is_r ? barR + ring : barS + ring;
+            if (tid == 0) mbar_arrive_expect_tx(bar, (unsigned)((is_r ? tm::R_MATS : tm::S_MATS) * tm::MAT_BYTES));
+            __syncwarp();
+            if (is_producer && b_isr == is_r) {
+                unsigned char* const dst = (is_r ? sR + ring * tm::R_BYTES : sS + ring * tm::S_BYTES) + b_base;
+                tma_load_4d(smem_u32(dst), &maps.m[b_shape], cx, cy, cz, tslot * 36 + b_lam * 9, bar);
+            }
         };
         auto t_up = [&](int t) { return (t == g.tloc - 1) ? g.t_up_wrap : t + 1; };
 
         // ---- prologue: slice tb (full) and the S part of slice tb+1; the backward-t staple of slice tb from global memory
-        copy_S(tb, 0);
-        copy_R(tb, 0);
-        copy_S(t_up(tb), 1);
-        cp_async_commit();
+        copy_part(0, tb, 0);
+        copy_part(1, tb, 0);
+        copy_part(0, t_up(tb), 1);
 
         Coord x;
         x.x = x0 + sx; x.y = y0 + sy; x.z = z0 + sz; x.t = tb;
@@ -218,25 +278,31 @@ __device__ __forceinline__ void tm_run(const Geom& g, const TmPlan& pl, const do
             const M3 C = load_link(uin, g, ym, 3);
             G = r2_mul_nn(r2_mul_nn(rows01_dag(A), U), C);
         }
-        cp_async_wait_all();
-        __syncthreads();
+        wait_bar(0);
+        wait_bar(tm::S_RING + 0);
+        wait_bar(1);
 
         int rs = 0;  // j % 3
         for (int j = 0; j < len; j++) {
             const int t = tb + j;
             const int rs1 = (rs == 2) ? 0 : rs + 1;   // (j+1) % 3
             const int rs2 = (rs1 == 2) ? 0 : rs1 + 1; // (j+2) % 3
-            if (j + 1 < len) {
-                copy_R(t + 1, (j + 1) & 1);
-                copy_S(t_up(t + 1), rs2);
+            const bool more = j + 1 < len;
+            if (more) {
+                copy_part(1, t + 1, (j + 1) & 1);
+                copy_part(0, t_up(t + 1), rs2);
             }
-            cp_async_commit();
 
             const unsigned char* const Sc = sS + rs * tm::S_BYTES;
             const unsigned char* const Sn = sS + rs1 * tm::S_BYTES;
             const unsigned char* const Rc = sR + (j & 1) * tm::R_BYTES;
-            auto cen = [&](int off) -> const unsigned char* { return ((off & 1) ? Rc : Sc) + (off & ~1); };
-            auto nxt = [&](int off) -> const unsigned char* { return Sn + (off & ~1); };
+            auto at = [&](int d) -> SmOp {
+                const int code = d >> 28;
+                SmOp o;
+                o.p = (code == 0 ? Sc : (code == 1 ? Rc : Sn)) + (d & 0xFFFF);
+                o.stride = (unsigned)((d >> 16) & 0xFF) * 16u;
+                return o;
+            };
 
             const unsigned zo = (unsigned)(t * 32 + MU * 8) * (unsigned)g.v3 + s3;
             const unsigned zsb = (unsigned)g.v3 * 8u;
@@ -246,71 +312,34 @@ __device__ __forceinline__ void tm_run(const Geom& g, const TmPlan& pl, const do
                 for (int k = 0; k < 8; k++) z[k] = __ldg(reinterpret_cast<const double*>(reinterpret_cast<const char*>(zin + zo) + (size_t)k * zsb));
             }
 
-            const M3 U = lds_m3(cen(op.own));
             M3 V;
-            R2 Gn;
             if (MU < 3) V = complete_su3(G);
             else V = m3_zero();
 #pragma unroll
             for (int jj = 0; jj < 3; jj++) {
-                const int nu = (MU + 1 + jj) & 3;
 #if GFB_TM_DEBUG == 1
-                m3_add(V, lds_m3(cen(op.up[jj][0])));
-                m3_add(V, lds_m3((MU < 3 && nu == 3) ? nxt(op.up[jj][1]) : cen(op.up[jj][1])));
-                m3_add(V, lds_m3((MU == 3) ? nxt(op.up[jj][2]) : cen(op.up[jj][2])));
-                if (nu < 3) {
-                    m3_add(V, lds_m3(cen(op.dn[jj][0])));
-                    m3_add(V, lds_m3(cen(op.dn[jj][1])));
-                    m3_add(V, lds_m3((MU == 3) ? nxt(op.dn[jj][2]) : cen(op.dn[jj][2])));
-                }
-                if (MU < 3) Gn = G;
+                m3_add(V, lds_m3(at(op.up[jj][0]))); m3_add(V, lds_m3(at(op.up[jj][1]))); m3_add(V, lds_m3(at(op.up[jj][2])));
+                m3_add(V, lds_m3(at(op.dn[jj][0]))); m3_add(V, lds_m3(at(op.dn[jj][1]))); m3_add(V, lds_m3(at(op.dn[jj][2])));
                 continue;
 #endif
-                if (MU < 3 && nu < 3) {
-                    {
-                        const R2 A = lds_rows01(cen(op.up[jj][0]));
-                        const M3 B = lds_m3(cen(op.up[jj][1]));
-                        const R2 T = r2_mul_nn(A, B);
-                        const M3 C = lds_m3(cen(op.up[jj][2]));
-                        acc_su3(V, r2_mul_nd(T, C));
-                    }
-                    {
-                        const R2 A = lds_dag_rows01(cen(op.dn[jj][0]));
-                        const M3 B = lds_m3(cen(op.dn[jj][1]));
-                        const R2 T = r2_mul_nn(A, B);
-                        const M3 C = lds_m3(cen(op.dn[jj][2]));
-                        acc_su3(V, r2_mul_nn(T, C));
-                    }
-                } else if (MU < 3) {  // nu = t: upper staple from slices t, t+1; the lower one was carried in G; next G from slice t
-                    const M3 A = lds_m3(cen(op.up[jj][0]));
-                    const M3 C = lds_m3(cen(op.up[jj][2]));
-                    {
-                        const M3 B = lds_m3(nxt(op.up[jj][1]));
-                        const R2 T = r2_mul_nn(rows01(A), B);
-                        acc_su3(V, r2_mul_nd(T, C));
-                    }
-                    {
-                        const R2 T = r2_mul_nn(rows01_dag(A), U);
-                        Gn = r2_mul_nn(T, C);
-                    }
-                } else {  // MU = t, nu spatial
-                    {
-                        const R2 A = lds_rows01(cen(op.up[jj][0]));
-                        const M3 B = lds_m3(cen(op.up[jj][1]));
-                        const R2 T = r2_mul_nn(A, B);
-                        const M3 C = lds_m3(nxt(op.up[jj][2]));
-                        acc_su3(V, r2_mul_nd(T, C));
-                    }
-                    {
-                        const R2 A = lds_dag_rows01(cen(op.dn[jj][0]));
-                        const M3 B = lds_m3(cen(op.dn[jj][1]));
-                        const R2 T = r2_mul_nn(A, B);
-                        const M3 C = lds_m3(nxt(op.dn[jj][2]));
-                        acc_su3(V, r2_mul_nn(T, C));
-                    }
+                {   // upper staple  A B C^dag
+                    const R2 A = lds_rows01(at(op.up[jj][0]));
+                    const M3 B = lds_m3(at(op.up[jj][1]));
+                    const R2 T = r2_mul_nn(A, B);
+                    const M3 C = lds_m3(at(op.up[jj][2]));
+                    acc_su3(V, r2_mul_nd(T, C));
+                }
+                {   // lower staple  A^dag B C  (for nu = t of a spatial link: the NEXT slice's one, carried in G)
+                    const R2 A = lds_dag_rows01(at(op.dn[jj][0]));
+                    const M3 B = lds_m3(at(op.dn[jj][1]));
+                    const R2 T = r2_mul_nn(A, B);
+                    const M3 C = lds_m3(at(op.dn[jj][2]));
+                    const R2 r = r2_mul_nn(T, C);
+                    if (jj == carry_j) G = r;
+                    else acc_su3(V, r);
                 }
             }
-            if (MU < 3) G = Gn;
+            const M3 U = lds_m3(at(op.own));
 
             double f[8];
             {
@@ -331,31 +360,39 @@ __device__ __forceinline__ void tm_run(const Geom& g, const TmPlan& pl, const do
                 m3_store(uout + uo, (unsigned)g.v3, r);
             }
 
-            cp_async_wait_all();
+            // the next slice's parts (requested at the top of this step) must have landed; then every thread is done
+            // reading this step's buffers and warp 0 may overwrite them
+            if (more) {
+                wait_bar(tm::S_RING + ((j + 1) & 1));
+                wait_bar(rs2);
+            }
             __syncthreads();
             rs = rs1;
         }
     }
 }
 
+constexpr size_t kTmBarOff = tm::SMEM_DATA;
+constexpr size_t kTmBoxOff = kTmBarOff + 8 * (tm::S_RING + tm::R_RING);
+
 template <bool READ_Z, bool WRITE_Z, bool DO_EXP>
 __global__ void __launch_bounds__(tm::NTHREADS, 1)
-k_tmarch_fused(Geom g, TmPlan pl, const double2* __restrict__ uin, double2* __restrict__ uout, const double* __restrict__ zin,
-               double* __restrict__ zout, double a, double b, double c) {
+k_tmarch_fused(const __grid_constant__ TmMaps maps, Geom g, TmPlan pl, const double2* __restrict__ uin, double2* __restrict__ uout,
+               const double* __restrict__ zin, double* __restrict__ zout, double a, double b, double c) {
     extern __shared__ __align__(128) unsigned char smem[];
-    tm::Box* const boxes = reinterpret_cast<tm::Box*>(smem + tm::SMEM_DATA);
-    if (threadIdx.x == 0) tm::make_boxes(boxes);
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + kTmBarOff);
+    tm::Box* const boxes = reinterpret_cast<tm::Box*>(smem + kTmBoxOff);
+    if (threadIdx.x == 0) {
+        tm::make_boxes(boxes);
+        for (int i = 0; i < tm::S_RING + tm::R_RING; i++) mbar_init(bars + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     const int mu = threadIdx.x / tm::SITES;  // warp-uniform: two warps per direction
-    switch (mu) {
-        case 0: tm_run<0, READ_Z, WRITE_Z, DO_EXP>(g, pl, uin, uout, zin, zout, a, b, c, smem, boxes); break;
-        case 1: tm_run<1, READ_Z, WRITE_Z, DO_EXP>(g, pl, uin, uout, zin, zout, a, b, c, smem, boxes); break;
-        case 2: tm_run<2, READ_Z, WRITE_Z, DO_EXP>(g, pl, uin, uout, zin, zout, a, b, c, smem, boxes); break;
-        default: tm_run<3, READ_Z, WRITE_Z, DO_EXP>(g, pl, uin, uout, zin, zout, a, b, c, smem, boxes); break;
-    }
+    tm_run<READ_Z, WRITE_Z, DO_EXP>(mu, maps, g, pl, uin, uout, zin, zout, a, b, c, smem, bars, boxes);
 }
 
-constexpr size_t kTmSmem = tm::SMEM_DATA + tm::NBOX * sizeof(tm::Box);
+constexpr size_t kTmSmem = kTmBoxOff + tm::NBOX * sizeof(tm::Box);
 
 // t-segments: enough (segment, tile) items to fill the SMs evenly, as few segment prologues as possible
 TmPlan make_plan(const Geom& g, int t_begin, int t_count, int nsm) {
@@ -377,6 +414,50 @@ TmPlan make_plan(const Geom& g, int t_begin, int t_count, int nsm) {
     pl.seg_len = (t_count + best_nseg - 1) / best_nseg;
     pl.nseg = (t_count + pl.seg_len - 1) / pl.seg_len;
     return pl;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// tensor maps of a link buffer viewed as [nslots*36 planes][nz][ny][2*nx doubles], one per box shape; cached per buffer
+const TmMaps* tensor_maps_for(const double2* u, const Geom& g) {
+    struct Key {
+        const void* p;
+        int nx, ny, nz, nslots;
+        bool operator==(const Key& o) const { return p == o.p && nx == o.nx && ny == o.ny && nz == o.nz && nslots == o.nslots; }
+    };
+    struct Hash {
+        size_t operator()(const Key& k) const {
+            return std::hash<const void*>()(k.p) ^ ((size_t)k.nx * 1315423911u) ^ ((size_t)k.ny << 12) ^ ((size_t)k.nz << 24) ^ ((size_t)k.nslots << 36);
+        }
+    };
+    static std::unordered_map<Key, TmMaps, Hash> cache;
+    static std::mutex mtx;
+    static EncodeTiledFn encode = nullptr;
+    std::lock_guard<std::mutex> lock(mtx);
+    const Key key{u, g.nx, g.ny, g.nz, g.nslots};
+    auto it = cache.find(key);
+    if (it != cache.end()) return &it->second;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return nullptr;
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    TmMaps maps;
+    const cuuint64_t gdim[4] = {(cuuint64_t)g.nx * 2, (cuuint64_t)g.ny, (cuuint64_t)g.nz, (cuuint64_t)g.nslots * 36};
+    const cuuint64_t gstride[3] = {(cuuint64_t)g.nx * 16, (cuuint64_t)g.nx * g.ny * 16, (cuuint64_t)g.v3 * 16};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    for (int s = 0; s < tm::NSHAPE; s++) {
+        int e[3];
+        tm::shape_extent(s, e);
+        const cuuint32_t box[4] = {(cuuint32_t)e[0] * 2, (cuuint32_t)e[1], (cuuint32_t)e[2], 9};
+        if (encode(&maps.m[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double2*>(u), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return nullptr;
+    }
+    if (cache.size() > 1024) cache.clear();  // buffers come and go with the fields; the maps are cheap to rebuild
+    return &cache.emplace(key, maps).first->second;
 }
 
 }  // namespace
@@ -402,6 +483,8 @@ bool launch_tmarch_fused(cudaStream_t st, const Geom& g, int t_begin, int t_coun
         const int len = atoi(e);
         if (len >= 1) { pl.seg_len = len < t_count ? len : t_count; pl.nseg = (t_count + pl.seg_len - 1) / pl.seg_len; }
     }
+    const TmMaps* maps = tensor_maps_for(uin, g);
+    if (!maps) return false;
     const long nitems = (long)pl.ntiles * pl.nseg;
     const unsigned grid = (unsigned)(nitems < nsm ? nitems : nsm);
 #define GFB_LAUNCH_TM(R, W, E)                                                                                                  \
@@ -415,7 +498,7 @@ bool launch_tmarch_fused(cudaStream_t st, const Geom& g, int t_begin, int t_coun
             }                                                                                                                   \
             attr_set = true;                                                                                                    \
         }                                                                                                                       \
-        kern<<<grid, tm::NTHREADS, kTmSmem, st>>>(g, pl, uin, uout, zin, zout, fa.a, fa.b, fa.c);                                \
+        kern<<<grid, tm::NTHREADS, kTmSmem, st>>>(*maps, g, pl, uin, uout, zin, zout, fa.a, fa.b, fa.c);                                \
     } while (0)
     if (fa.read_z) {
         if (fa.do_exp) GFB_LAUNCH_TM(true, true, true);

@@ -10,11 +10,14 @@
 //   * of slice t+1 only the spatial links on the tile and on the -e_lam face.
 // The backward-t staple of slice t is carried in registers from slice t-1 (the same thread computed it there),
 // so slice t-1 is never resident.  The full set is split in two parts with separate rings:
-//   S part  (248 matrices)  spatial lam on the box  tile extended by one site towards -e_lam    [needed as t+1 AND as t]
+//   S part  (248 matrices)  spatial lam on the tile and on its -e_lam face                     [needed as t+1 AND as t]
 //   R part  (428 matrices)  everything else                                                    [needed only as t]
-// Ring depth: S 3 (t, t+1 and the t+2 being fetched), R 2 (t and the t+1 being fetched): 1600 matrices = 230400 bytes.
-// Inside a part a matrix is 144 contiguous bytes (array of structures): the 8 x-consecutive lanes of an LDS.128 phase
-// hit stride-9 16-byte groups, which is conflict-free.
+// Ring depth: S 3 (t, t+1 and the t+2 being fetched), R 2 (t and the t+1 being fetched).
+// Every part is a list of BOXES (31 per slice), each fetched by one TMA tensor copy of 9 element planes
+// (cp.async.bulk.tensor.4d, box = 2*ex doubles x ey x ez x 9 planes); a box never crosses the periodic boundary because it is
+// either inside the tile's extent or a single halo layer in each direction, so its origin is wrapped per coordinate.
+// Inside a box the layout is the copy's: [k][z][y][x] 16-byte elements, i.e. element k of the matrix at box position i sits at
+// box_base + (k*n + i)*16 with n the box volume: the 8 x-consecutive lanes of an LDS.128 phase read 128 contiguous bytes.
 #pragma once
 
 #if defined(__CUDACC__)
@@ -32,101 +35,100 @@ constexpr int BX = 8, BY = 4, BZ = 2;
 constexpr int SITES = BX * BY * BZ;      // 64 sites, 256 link-threads
 constexpr int NTHREADS = 4 * SITES;
 constexpr int MAT_BYTES = 144;
-constexpr int NBOX = 22;
+constexpr int NBOX = 31;
+constexpr int NSHAPE = 7;
 constexpr int S_MATS = 248, R_MATS = 428;
-constexpr int S_BYTES = S_MATS * MAT_BYTES, R_BYTES = R_MATS * MAT_BYTES;
+constexpr int S_BYTES = 35712;           // 248 matrices, every S box is a multiple of 8 matrices (no padding)
+constexpr int R_BYTES = 61952;           // 428 matrices + 320 bytes of padding (box bases are 128-byte aligned for TMA)
 constexpr int S_RING = 3, R_RING = 2;
-constexpr int SMEM_DATA = S_RING * S_BYTES + R_RING * R_BYTES;  // 230400
+constexpr int SMEM_DATA = S_RING * S_BYTES + R_RING * R_BYTES;  // 231040
 
 struct Box {
     signed char lam, is_r;
     signed char o[3];  // origin relative to the tile origin (-1 .. B)
     signed char e[3];  // extents
-    short base;        // first slot inside its part
+    int base;          // byte offset inside its part (128-byte aligned)
 };
 
 TM_HD int tile_extent(int d) { return d == 0 ? BX : d == 1 ? BY : BZ; }
+TM_HD int box_volume(const Box& b) { return b.e[0] * b.e[1] * b.e[2]; }
+TM_HD int pad128(int n) { return (n + 127) & ~127; }
+// index of the box shape among the NSHAPE distinct (ex, ey, ez): one tensor map per shape
+TM_HD int shape_index(int ex, int ey, int ez) {
+    if (ex == BX && ey == BY && ez == BZ) return 0;
+    if (ex == 1 && ey == BY && ez == BZ) return 1;
+    if (ex == BX && ey == 1 && ez == BZ) return 2;
+    if (ex == BX && ey == BY && ez == 1) return 3;
+    if (ex == 1 && ey == 1 && ez == BZ) return 4;
+    if (ex == 1 && ey == BY && ez == 1) return 5;
+    if (ex == BX && ey == 1 && ez == 1) return 6;
+    return -1;
+}
+TM_HD void shape_extent(int s, int* e) {
+    e[0] = (s == 1 || s == 4 || s == 5) ? 1 : BX;
+    e[1] = (s == 2 || s == 4 || s == 6) ? 1 : BY;
+    e[2] = (s == 3 || s == 5 || s == 6) ? 1 : BZ;
+}
 
-// Fills the 22 boxes: 3 S boxes (lam = 0,1,2), then R boxes: per spatial lam [+i1, +i2, -i1, -i2] (i1 < i2 the other two
-// spatial directions), then lam = 3: tile, +x, +y, +z, -x, -y, -z.  Returns the number of boxes.
-TM_HD int make_boxes(Box* b) {
-    int n = 0;
-    int sbase = 0, rbase = 0;
-    for (int lam = 0; lam < 3; lam++) {
-        Box x;
-        x.lam = (signed char)lam; x.is_r = 0;
-        for (int d = 0; d < 3; d++) { x.o[d] = (signed char)(d == lam ? -1 : 0); x.e[d] = (signed char)(tile_extent(d) + (d == lam ? 1 : 0)); }
-        x.base = (short)sbase;
-        sbase += x.e[0] * x.e[1] * x.e[2];
-        b[n++] = x;
+// Fills the NBOX boxes.  A box is described by the set of directions in which it is a halo layer:
+//   lo[d] = -1 / +1  -> the single layer at -1 / at B_d ;  0 -> the tile's extent in d
+TM_HD void put_box(Box* b, int* n, int* sbase, int* rbase, int lam, int is_r, int l0, int l1, int l2) {
+    const int lo[3] = {l0, l1, l2};
+    Box x;
+    x.lam = (signed char)lam; x.is_r = (signed char)is_r;
+    for (int d = 0; d < 3; d++) {
+        x.o[d] = (signed char)(lo[d] < 0 ? -1 : (lo[d] > 0 ? tile_extent(d) : 0));
+        x.e[d] = (signed char)(lo[d] != 0 ? 1 : tile_extent(d));
     }
-    for (int lam = 0; lam < 3; lam++) {
-        for (int sgn = +1; sgn >= -1; sgn -= 2) {
-            for (int i = 0; i < 3; i++) {
-                if (i == lam) continue;
-                Box x;
-                x.lam = (signed char)lam; x.is_r = 1;
-                for (int d = 0; d < 3; d++) {
-                    if (d == i) { x.o[d] = (signed char)(sgn > 0 ? tile_extent(d) : -1); x.e[d] = 1; }
-                    else if (d == lam && sgn > 0) { x.o[d] = -1; x.e[d] = (signed char)(tile_extent(d) + 1); }
-                    else { x.o[d] = 0; x.e[d] = (signed char)tile_extent(d); }
-                }
-                x.base = (short)rbase;
-                rbase += x.e[0] * x.e[1] * x.e[2];
-                b[n++] = x;
-            }
+    int* base = is_r ? rbase : sbase;
+    x.base = *base;
+    *base += pad128(box_volume(x) * MAT_BYTES);
+    b[(*n)++] = x;
+}
+TM_HD int make_boxes(Box* b) {
+    int n = 0, sbase = 0, rbase = 0;
+    for (int lam = 0; lam < 3; lam++) {  // S part: tile and the -e_lam layer
+        put_box(b, &n, &sbase, &rbase, lam, 0, 0, 0, 0);
+        put_box(b, &n, &sbase, &rbase, lam, 0, lam == 0 ? -1 : 0, lam == 1 ? -1 : 0, lam == 2 ? -1 : 0);
+    }
+    for (int lam = 0; lam < 3; lam++) {  // R part of a spatial direction
+        for (int i = 0; i < 3; i++) {
+            if (i == lam) continue;
+            int l[3] = {0, 0, 0};
+            l[i] = +1;                     // +e_i face ...
+            put_box(b, &n, &sbase, &rbase, lam, 1, l[0], l[1], l[2]);
+            l[lam] = -1;                   // ... and its (+e_i, -e_lam) edge
+            put_box(b, &n, &sbase, &rbase, lam, 1, l[0], l[1], l[2]);
+        }
+        for (int i = 0; i < 3; i++) {
+            if (i == lam) continue;
+            int l[3] = {0, 0, 0};
+            l[i] = -1;                     // -e_i face
+            put_box(b, &n, &sbase, &rbase, lam, 1, l[0], l[1], l[2]);
         }
     }
-    {
-        Box x;
-        x.lam = 3; x.is_r = 1;
-        for (int d = 0; d < 3; d++) { x.o[d] = 0; x.e[d] = (signed char)tile_extent(d); }
-        x.base = (short)rbase;
-        rbase += SITES;
-        b[n++] = x;
-        for (int sgn = +1; sgn >= -1; sgn -= 2)
-            for (int i = 0; i < 3; i++) {
-                Box y;
-                y.lam = 3; y.is_r = 1;
-                for (int d = 0; d < 3; d++) {
-                    if (d == i) { y.o[d] = (signed char)(sgn > 0 ? tile_extent(d) : -1); y.e[d] = 1; }
-                    else { y.o[d] = 0; y.e[d] = (signed char)tile_extent(d); }
-                }
-                y.base = (short)rbase;
-                rbase += y.e[0] * y.e[1] * y.e[2];
-                b[n++] = y;
-            }
-    }
+    put_box(b, &n, &sbase, &rbase, 3, 1, 0, 0, 0);  // U_t: tile and the six faces
+    for (int sgn = +1; sgn >= -1; sgn -= 2)
+        for (int i = 0; i < 3; i++) {
+            int l[3] = {0, 0, 0};
+            l[i] = sgn;
+            put_box(b, &n, &sbase, &rbase, 3, 1, l[0], l[1], l[2]);
+        }
     return n;
 }
 
-// byte offset (within its part) of link lam at tile-relative position (x, y, z), bit 0 set when it lives in the R part;
-// -1 when the position is not resident (never happens for the stencil's operands: checked by the host checker)
+// operand descriptor of link lam at tile-relative position (x, y, z):
+//   bits 0-15 byte offset of element 0 inside its part, bits 16-23 box volume n (element k is k*n*16 bytes further),
+//   bit 24 set when the box belongs to the R part;  -1 when the position is not resident
 TM_HD int lookup(const Box* b, int lam, int x, int y, int z) {
     for (int i = 0; i < NBOX; i++) {
         if (b[i].lam != lam) continue;
         const int dx = x - b[i].o[0], dy = y - b[i].o[1], dz = z - b[i].o[2];
         if (dx < 0 || dy < 0 || dz < 0 || dx >= b[i].e[0] || dy >= b[i].e[1] || dz >= b[i].e[2]) continue;
-        const int slot = b[i].base + dx + b[i].e[0] * (dy + b[i].e[1] * dz);
-        return slot * MAT_BYTES + (b[i].is_r ? 1 : 0);
+        const int idx = dx + b[i].e[0] * (dy + b[i].e[1] * dz);
+        return (b[i].base + idx * 16) | (box_volume(b[i]) << 16) | ((b[i].is_r ? 1 : 0) << 24);
     }
     return -1;
-}
-
-// inverse map used by the producer: slot m of part `is_r` -> (lam, x, y, z); returns false past the end of the part
-TM_HD bool slot_to_pos(const Box* b, int is_r, int m, int* lam, int* x, int* y, int* z) {
-    for (int i = 0; i < NBOX; i++) {
-        if (b[i].is_r != is_r) continue;
-        const int n = b[i].e[0] * b[i].e[1] * b[i].e[2];
-        const int r = m - b[i].base;
-        if (r < 0 || r >= n) continue;
-        *lam = b[i].lam;
-        *x = b[i].o[0] + r % b[i].e[0];
-        *y = b[i].o[1] + (r / b[i].e[0]) % b[i].e[1];
-        *z = b[i].o[2] + r / (b[i].e[0] * b[i].e[1]);
-        return true;
-    }
-    return false;
 }
 
 // Operand table of link-thread (site, mu).  For j = 0..2, nu = (mu+1+j) & 3:
@@ -134,7 +136,7 @@ TM_HD bool slot_to_pos(const Box* b, int is_r, int m, int* lam, int* x, int* y, 
 //   lower staple  A^dag B C   with A = U_nu(x-nu), B = U_mu(x-nu), C = U_nu(x-nu+mu)     (nu spatial only; nu = t is carried)
 // Which slice an operand lives in follows from (mu, nu) alone:  a +t shift -> S part of slice t+1, otherwise slice t.
 struct Operands {
-    int up[3][3];  // [j][A,B,C] byte offset | is_r
+    int up[3][3];  // [j][A,B,C] descriptors (lookup())
     int dn[3][3];
     int own;
 };

@@ -22,30 +22,45 @@ int main(int argc, char** argv) {
     const int seg_len = atoi(argv[5]);
     Box boxes[NBOX];
     if (make_boxes(boxes) != NBOX) { printf("box count\n"); return 1; }
-    // part sizes
+    // part sizes, alignment, shapes
     {
-        int s = 0, r = 0;
+        int s = 0, r = 0, sm = 0, rm = 0;
         for (int i = 0; i < NBOX; i++) {
-            int n = boxes[i].e[0] * boxes[i].e[1] * boxes[i].e[2];
-            if (boxes[i].is_r) { if (boxes[i].base != r) { printf("R base\n"); return 1; } r += n; }
-            else { if (boxes[i].base != s) { printf("S base\n"); return 1; } s += n; }
+            const int n = box_volume(boxes[i]);
+            int& base = boxes[i].is_r ? r : s;
+            if (boxes[i].base != base || (base & 127)) { printf("box base %d\n", i); return 1; }
+            base += pad128(n * MAT_BYTES);
+            (boxes[i].is_r ? rm : sm) += n;
+            const int sh = shape_index(boxes[i].e[0], boxes[i].e[1], boxes[i].e[2]);
+            int e[3];
+            if (sh < 0) { printf("box shape %d\n", i); return 1; }
+            shape_extent(sh, e);
+            if (e[0] != boxes[i].e[0] || e[1] != boxes[i].e[1] || e[2] != boxes[i].e[2]) { printf("shape_extent %d\n", i); return 1; }
+            // a box never crosses the periodic boundary: inside the tile's extent or a single layer
+            for (int d = 0; d < 3; d++)
+                if (!((boxes[i].o[d] == 0 && boxes[i].e[d] == tile_extent(d)) || (boxes[i].e[d] == 1 && (boxes[i].o[d] == -1 || boxes[i].o[d] == tile_extent(d))))) { printf("box %d spans\n", i); return 1; }
         }
-        if (s != S_MATS || r != R_MATS) { printf("part sizes %d %d\n", s, r); return 1; }
+        if (s != S_BYTES || r != R_BYTES || sm != S_MATS || rm != R_MATS) { printf("part sizes %d %d %d %d\n", s, r, sm, rm); return 1; }
+        if (R_BYTES >= 65536) { printf("descriptor offset overflow\n"); return 1; }
     }
-    std::vector<long> S(S_RING * S_MATS, -1), R(R_RING * R_MATS, -1);
+    // shared memory as 16-byte elements holding (link id * 9 + k)
+    std::vector<long> S(S_RING * S_BYTES / 16, -1), R(R_RING * R_BYTES / 16, -1);
     long checked = 0;
     const int nseg = (NTg + seg_len - 1) / seg_len;
     for (int z0 = 0; z0 < NZg; z0 += BZ) for (int y0 = 0; y0 < NYg; y0 += BY) for (int x0 = 0; x0 < NXg; x0 += BX)
     for (int seg = 0; seg < nseg; seg++) {
         const int tb = seg * seg_len;
         const int len = (seg_len < NTg - tb) ? seg_len : NTg - tb;
+        // one TMA tensor copy per box: origin wrapped per coordinate, box-dense destination [k][z][y][x]
         auto copy_part = [&](int is_r, int t, int ring) {
-            const int n = is_r ? R_MATS : S_MATS;
-            for (int m = 0; m < n + 40; m++) {  // the kernel probes slots tid and tid+256 past the end as well
-                int lam, x, y, z;
-                if (!slot_to_pos(boxes, is_r, m, &lam, &x, &y, &z)) { if (m < n) { printf("slot_to_pos hole\n"); exit(1); } continue; }
-                if (m >= n) { printf("slot_to_pos past end\n"); exit(1); }
-                (is_r ? R : S)[ring * n + m] = link_id(lam, x0 + x, y0 + y, z0 + z, t);
+            for (int i = 0; i < NBOX; i++) {
+                const Box& b = boxes[i];
+                if (b.is_r != is_r) continue;
+                const int ox = wrapc(x0 + b.o[0], NXg), oy = wrapc(y0 + b.o[1], NYg), oz = wrapc(z0 + b.o[2], NZg);
+                if (ox + b.e[0] > NXg || oy + b.e[1] > NYg || oz + b.e[2] > NZg) { printf("box crosses the boundary\n"); exit(1); }
+                long* dst = (is_r ? R.data() + (size_t)ring * R_BYTES / 16 : S.data() + (size_t)ring * S_BYTES / 16) + b.base / 16;
+                for (int k = 0; k < 9; k++) for (int z = 0; z < b.e[2]; z++) for (int y = 0; y < b.e[1]; y++) for (int x = 0; x < b.e[0]; x++)
+                    *dst++ = link_id(b.lam, ox + x, oy + y, oz + z, t) * 9 + k;
             }
         };
         copy_part(0, tb, 0); copy_part(1, tb, 0); copy_part(0, tb + 1, 1);
@@ -54,8 +69,19 @@ int main(int argc, char** argv) {
             const int t = tb + j;
             const int rs1 = (rs + 1) % 3, rs2 = (rs1 + 1) % 3;
             // emulate the asynchronous prefetch landing at the END of the step: read first, copy afterwards
-            auto cen = [&](int off) { if (off < 0) { printf("missing operand\n"); exit(1); } return (off & 1) ? R[(j & 1) * R_MATS + (off >> 1) / (MAT_BYTES / 2)] : S[rs * S_MATS + off / MAT_BYTES]; };
-            auto nxt = [&](int off) { if (off < 0 || (off & 1)) { printf("next-slice operand not in S\n"); exit(1); } return S[rs1 * S_MATS + off / MAT_BYTES]; };
+            // an operand is read as 9 elements at stride n*16 bytes; all nine must be the same link, k = 0..8 in order
+            auto fetch = [&](const std::vector<long>& part, size_t part_base16, int d) {
+                const int off = d & 0xFFFF, n = (d >> 16) & 0xFF;
+                long id = -1;
+                for (int k = 0; k < 9; k++) {
+                    const long v = part[part_base16 + (off + k * n * 16) / 16];
+                    if (v < 0 || v % 9 != k || (k > 0 && v / 9 != id)) { printf("bad element k=%d\n", k); exit(1); }
+                    id = v / 9;
+                }
+                return id;
+            };
+            auto cen = [&](int d) { if (d < 0) { printf("missing operand\n"); exit(1); } return ((d >> 24) & 1) ? fetch(R, (size_t)(j & 1) * R_BYTES / 16, d) : fetch(S, (size_t)rs * S_BYTES / 16, d); };
+            auto nxt = [&](int d) { if (d < 0 || ((d >> 24) & 1)) { printf("next-slice operand not in S\n"); exit(1); } return fetch(S, (size_t)rs1 * S_BYTES / 16, d); };
             for (int mu = 0; mu < 4; mu++) for (int sz = 0; sz < BZ; sz++) for (int sy = 0; sy < BY; sy++) for (int sx = 0; sx < BX; sx++) {
                 Operands op;
                 make_operands(boxes, sx, sy, sz, mu, &op);
