@@ -270,7 +270,9 @@ def main():
         kern, kern_bytes = "k_update_links + k_force_fused<kick> + k_update_links (whole QPQ step)", (2 * (P_BYTES + 2 * U_BYTES) + U_BYTES + 2 * P_BYTES)
         kern_ms = ms / K
     else:
-        kern, kern_bytes = "k_force_fused<READ_Z,WRITE_Z,DO_EXP> (staple->TA force->momentum kick->exp(eps P) U)", 2 * U_BYTES + 2 * P_BYTES
+        tiled = nx % 8 == 0 and ny % 4 == 0 and nz % 2 == 0 and os.environ.get("GFB200_TMARCH", "1") != "0"
+        kern = ("k_tmarch_fused<READ_Z,WRITE_Z,DO_EXP>" if tiled else "k_force_fused<READ_Z,WRITE_Z,DO_EXP>") + " (staple->TA force->momentum kick->exp(eps P) U)"
+        kern_bytes = 2 * U_BYTES + 2 * P_BYTES
         kern_ms = max(ms - t_extra, 1e-9) / K
     achieved = kern_bytes * sites_local / (kern_ms * 1e-3) / 1e9
     traffic = None
@@ -278,7 +280,8 @@ def main():
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
-            traffic = tj["k_force_fused_bytes_per_site"] * sites_local  # ncu dram bytes per site (measured at tj["lattice"]) x this launch's sites
+            key = "k_tmarch_fused_bytes_per_site" if kern.startswith("k_tmarch") and "k_tmarch_fused_bytes_per_site" in tj else "k_force_fused_bytes_per_site"
+            traffic = tj[key] * sites_local  # ncu dram bytes per site (measured at tj["lattice"]) x this launch's sites
         except Exception:
             traffic = None
 

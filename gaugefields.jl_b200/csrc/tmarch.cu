@@ -84,12 +84,16 @@ __device__ __forceinline__ void tma_load_4d(unsigned dst_smem, const CUtensorMap
 #endif
 }
 
-// operand in shared memory: element k at p + k*stride (box-dense [k][pos] layout, tmarch_geom.h)
+// operand in shared memory: element k at p + k*stride (box-dense [k][pos] layout, tmarch_geom.h); p is a 32-bit shared address
 struct SmOp {
-    const unsigned char* p;
+    unsigned p;
     unsigned stride;
 };
-__device__ __forceinline__ double2 lds_el(const SmOp& o, int k) { return *reinterpret_cast<const double2*>(o.p + k * o.stride); }
+__device__ __forceinline__ double2 lds_el(const SmOp& o, int k) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(o.p + k * o.stride));
+    return v;
+}
 __device__ __forceinline__ M3 lds_m3(const SmOp& o) {
     M3 r;
 #pragma unroll
@@ -112,6 +116,12 @@ __device__ __forceinline__ R2 lds_dag_rows01(const SmOp& o) {
             const double2 v = lds_el(o, 3 * j + i);
             r.e[3 * i + j] = make_double2(v.x, -v.y);
         }
+    return r;
+}
+__device__ __forceinline__ R2 rows01(const M3& a) {
+    R2 r;
+#pragma unroll
+    for (int k = 0; k < 6; k++) r.e[k] = a.e[k];
     return r;
 }
 __device__ __forceinline__ R2 rows01_dag(const M3& a) {
@@ -190,34 +200,26 @@ __device__ __forceinline__ void tm_run(const int MU, const TmMaps& maps, const G
     unsigned char* const sS = smem;
     unsigned char* const sR = smem + tm::S_RING * tm::S_BYTES;
 
-    // ---- consumer side: operand descriptors (tile independent): tm::lookup() bits 0-24, ring code in bits 28-29
-    //      (0: S part of slice t, 1: R part of slice t, 2: S part of slice t+1)
+    // ---- consumer side: operand descriptors (tile independent): tm::lookup() bits 0-23 (offset, box volume),
+    //      bit 28: R part of slice t, bit 29: S part of slice t+1 (neither: S part of slice t)
     tm::Operands op;
     tm::make_operands(boxes, sx, sy, sz, MU, &op);
-    const int carry_j = (MU < 3) ? 2 - MU : -1;  // the iteration with nu = t of a spatial link
     {
         auto cen = [](int d) { return (d & 0xFFFFFF) | (((d >> 24) & 1) << 28); };
         auto nxt = [](int d) { return (d & 0xFFFFFF) | (2 << 28); };
-        const int own = cen(op.own);
+        op.own = cen(op.own);
 #pragma unroll
         for (int jj = 0; jj < 3; jj++) {
-            const int nu = (MU + 1 + jj) & 3;
-            const int a0 = cen(op.up[jj][0]);
-            const int b0 = (MU < 3 && nu == 3) ? nxt(op.up[jj][1]) : cen(op.up[jj][1]);
-            const int c0 = (MU == 3) ? nxt(op.up[jj][2]) : cen(op.up[jj][2]);
-            int a1, b1, c1;
-            if (jj == carry_j) {
-                // next slice's backward-t staple  U_t(x)^dag U_mu(x) U_t(x+mu): same shape as a lower staple, operands from slice t
-                a1 = a0; b1 = own; c1 = c0;
-            } else {
-                a1 = cen(op.dn[jj][0]);
-                b1 = cen(op.dn[jj][1]);
-                c1 = (MU == 3) ? nxt(op.dn[jj][2]) : cen(op.dn[jj][2]);
+            const int nu = tm::staple_dir(MU, jj);
+            op.up[jj][0] = cen(op.up[jj][0]);
+            op.up[jj][1] = (MU < 3 && nu == 3) ? nxt(op.up[jj][1]) : cen(op.up[jj][1]);
+            op.up[jj][2] = (MU == 3) ? nxt(op.up[jj][2]) : cen(op.up[jj][2]);
+            if (nu < 3) {
+                op.dn[jj][0] = cen(op.dn[jj][0]);
+                op.dn[jj][1] = cen(op.dn[jj][1]);
+                op.dn[jj][2] = (MU == 3) ? nxt(op.dn[jj][2]) : cen(op.dn[jj][2]);
             }
-            op.up[jj][0] = a0; op.up[jj][1] = b0; op.up[jj][2] = c0;
-            op.dn[jj][0] = a1; op.dn[jj][1] = b1; op.dn[jj][2] = c1;
         }
-        op.own = own;
     }
 
     // ---- producer side: lane b of warp 0 owns box b (31 boxes per slice)
@@ -293,14 +295,15 @@ __device__ __forceinline__ void tm_run(const int MU, const TmMaps& maps, const G
                 copy_part(0, t_up(t + 1), rs2);
             }
 
-            const unsigned char* const Sc = sS + rs * tm::S_BYTES;
-            const unsigned char* const Sn = sS + rs1 * tm::S_BYTES;
-            const unsigned char* const Rc = sR + (j & 1) * tm::R_BYTES;
+            // branch-free operand addressing (a ternary on the three ring bases compiled to divergent-branch regions that
+            // ptxas could not schedule loads across): 32-bit shared address = Sc + offset + isR*(Rc-Sc) + isNext*(Sn-Sc)
+            const unsigned sc = smem_u32(sS + rs * tm::S_BYTES);
+            const unsigned d_r = smem_u32(sR + (j & 1) * tm::R_BYTES) - sc;
+            const unsigned d_n = smem_u32(sS + rs1 * tm::S_BYTES) - sc;
             auto at = [&](int d) -> SmOp {
-                const int code = d >> 28;
                 SmOp o;
-                o.p = (code == 0 ? Sc : (code == 1 ? Rc : Sn)) + (d & 0xFFFF);
-                o.stride = (unsigned)((d >> 16) & 0xFF) * 16u;
+                o.p = sc + ((unsigned)d & 0xFFFFu) + (((unsigned)d >> 28) & 1u) * d_r + (((unsigned)d >> 29) & 1u) * d_n;
+                o.stride = (((unsigned)d >> 16) & 0xFFu) * 16u;
                 return o;
             };
 
@@ -312,34 +315,51 @@ __device__ __forceinline__ void tm_run(const int MU, const TmMaps& maps, const G
                 for (int k = 0; k < 8; k++) z[k] = __ldg(reinterpret_cast<const double*>(reinterpret_cast<const char*>(zin + zo) + (size_t)k * zsb));
             }
 
-            M3 V;
+            M3 V, U;
             if (MU < 3) V = complete_su3(G);
             else V = m3_zero();
+#if GFB_TM_DEBUG == 1
 #pragma unroll
             for (int jj = 0; jj < 3; jj++) {
-#if GFB_TM_DEBUG == 1
                 m3_add(V, lds_m3(at(op.up[jj][0]))); m3_add(V, lds_m3(at(op.up[jj][1]))); m3_add(V, lds_m3(at(op.up[jj][2])));
-                m3_add(V, lds_m3(at(op.dn[jj][0]))); m3_add(V, lds_m3(at(op.dn[jj][1]))); m3_add(V, lds_m3(at(op.dn[jj][2])));
-                continue;
-#endif
-                {   // upper staple  A B C^dag
-                    const R2 A = lds_rows01(at(op.up[jj][0]));
-                    const M3 B = lds_m3(at(op.up[jj][1]));
-                    const R2 T = r2_mul_nn(A, B);
-                    const M3 C = lds_m3(at(op.up[jj][2]));
+                if (jj < 2 || MU == 3) { m3_add(V, lds_m3(at(op.dn[jj][0]))); m3_add(V, lds_m3(at(op.dn[jj][1]))); m3_add(V, lds_m3(at(op.dn[jj][2]))); }
+            }
+            U = lds_m3(at(op.own));
+#else
+            auto upper = [&](int jj) {  // A B C^dag
+                const R2 A = lds_rows01(at(op.up[jj][0]));
+                const M3 B = lds_m3(at(op.up[jj][1]));
+                const R2 T = r2_mul_nn(A, B);
+                const M3 C = lds_m3(at(op.up[jj][2]));
+                acc_su3(V, r2_mul_nd(T, C));
+            };
+            auto lower = [&](int jj) {  // A^dag B C
+                const R2 A = lds_dag_rows01(at(op.dn[jj][0]));
+                const M3 B = lds_m3(at(op.dn[jj][1]));
+                const R2 T = r2_mul_nn(A, B);
+                const M3 C = lds_m3(at(op.dn[jj][2]));
+                acc_su3(V, r2_mul_nn(T, C));
+            };
+            upper(0); lower(0);
+            upper(1); lower(1);
+            if (MU == 3) {
+                upper(2); lower(2);
+                U = lds_m3(at(op.own));
+            } else {
+                // nu = t: the upper staple U_t(x) U_mu(x+t) U_t(x+mu)^dag and the NEXT slice's backward staple
+                // U_t(x)^dag U_mu(x) U_t(x+mu) share A = U_t(x) and C = U_t(x+mu); B of the latter is the own link
+                const M3 A = lds_m3(at(op.up[2][0]));
+                const M3 C = lds_m3(at(op.up[2][2]));
+                {
+                    const M3 B = lds_m3(at(op.up[2][1]));
+                    const R2 T = r2_mul_nn(rows01(A), B);
                     acc_su3(V, r2_mul_nd(T, C));
                 }
-                {   // lower staple  A^dag B C  (for nu = t of a spatial link: the NEXT slice's one, carried in G)
-                    const R2 A = lds_dag_rows01(at(op.dn[jj][0]));
-                    const M3 B = lds_m3(at(op.dn[jj][1]));
-                    const R2 T = r2_mul_nn(A, B);
-                    const M3 C = lds_m3(at(op.dn[jj][2]));
-                    const R2 r = r2_mul_nn(T, C);
-                    if (jj == carry_j) G = r;
-                    else acc_su3(V, r);
-                }
+                U = lds_m3(at(op.own));
+                const R2 T = r2_mul_nn(rows01_dag(A), U);
+                G = r2_mul_nn(T, C);
             }
-            const M3 U = lds_m3(at(op.own));
+#endif
 
             double f[8];
             {

@@ -131,7 +131,11 @@ TM_HD int lookup(const Box* b, int lam, int x, int y, int z) {
     return -1;
 }
 
-// Operand table of link-thread (site, mu).  For j = 0..2, nu = (mu+1+j) & 3:
+// j-th staple direction of a link in direction mu: the other three directions in ascending order, so that nu = t is the LAST
+// iteration of a spatial link (the kernel fuses it with the carried backward-t staple)
+TM_HD int staple_dir(int mu, int j) { return j < mu ? j : j + 1; }
+
+// Operand table of link-thread (site, mu).  For j = 0..2, nu = staple_dir(mu, j):
 //   upper staple  A B C^dag   with A = U_nu(x), B = U_mu(x+nu), C = U_nu(x+mu)
 //   lower staple  A^dag B C   with A = U_nu(x-nu), B = U_mu(x-nu), C = U_nu(x-nu+mu)     (nu spatial only; nu = t is carried)
 // Which slice an operand lives in follows from (mu, nu) alone:  a +t shift -> S part of slice t+1, otherwise slice t.
@@ -151,7 +155,7 @@ TM_HD void make_operands(const Box* b, int sx, int sy, int sz, int mu, Operands*
     o->own = lookup(b, mu, sx, sy, sz);
     TM_UNROLL
     for (int j = 0; j < 3; j++) {
-        const int nu = (mu + 1 + j) & 3;
+        const int nu = staple_dir(mu, j);
         // shifts along t select the slice (compile-time in the kernel); here only the spatial part of the shift matters
         o->up[j][0] = shifted(b, nu, p, -1, -1);
         o->up[j][1] = shifted(b, mu, p, nu, -1);

@@ -96,7 +96,7 @@ int main(int argc, char** argv) {
 #define EXPECT(got, want, what) do { if ((got) != (want)) { printf("mismatch %s mu=%d site=%d,%d,%d t=%d tile=%d,%d,%d got %ld want %ld\n", what, mu, sx, sy, sz, t, x0, y0, z0, (long)(got), (long)(want)); return 1; } checked++; } while (0)
                 EXPECT(cen(op.own), id(mu, -1, -1), "own");
                 for (int jj = 0; jj < 3; jj++) {
-                    const int nu = (mu + 1 + jj) & 3;
+                    const int nu = staple_dir(mu, jj);
                     if (mu < 3 && nu < 3) {
                         EXPECT(cen(op.up[jj][0]), id(nu, -1, -1), "upA");
                         EXPECT(cen(op.up[jj][1]), id(mu, nu, -1), "upB");
