@@ -316,8 +316,10 @@ static bool launch_rowtile_nx(cudaStream_t st, const Geom& g, int t_begin, int t
 #define GFB_LAUNCH_RT(R, W, E)                                                                                            \
     do {                                                                                                                  \
         auto kern = k_rowtile_fused<NXW, R, W, E>;                                                                        \
-        static bool attr_set = false;                                                                                     \
-        if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; } \
+        static bool attr_set[64] = {};  /* per device */                                                                   \
+        int dev_ = 0;                                                                                                     \
+        cudaGetDevice(&dev_);                                                                                             \
+        if (!attr_set[dev_ & 63]) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set[dev_ & 63] = true; } \
         kern<<<grid, block, smem, st>>>(*tm, g, t_begin, t_count, uout, zin, zout, fa.a, fa.b, fa.c);                      \
     } while (0)
     if (fa.read_z) {

@@ -193,43 +193,24 @@ __device__ __forceinline__ int wrap(int c, int n) { return c < 0 ? c + n : (c >=
 template <bool READ_Z, bool WRITE_Z, bool DO_EXP>
 __device__ __forceinline__ void tm_run(const int MU, const TmMaps& maps, const Geom& g, const TmPlan& pl, const double2* __restrict__ uin,
                                        double2* __restrict__ uout, const double* __restrict__ zin, double* __restrict__ zout, double a, double b,
-                                       double c, unsigned char* smem, uint64_t* bars, const tm::Box* boxes) {
+                                       double c, unsigned char* smem, uint64_t* bars, const tm::Tables* __restrict__ tab) {
     const int tid = threadIdx.x;
     const int sidx = tid & (tm::SITES - 1);
     const int sx = sidx & (tm::BX - 1), sy = (sidx / tm::BX) & (tm::BY - 1), sz = sidx / (tm::BX * tm::BY);
     unsigned char* const sS = smem;
     unsigned char* const sR = smem + tm::S_RING * tm::S_BYTES;
 
-    // ---- consumer side: operand descriptors (tile independent): tm::lookup() bits 0-23 (offset, box volume),
-    //      bit 28: R part of slice t, bit 29: S part of slice t+1 (neither: S part of slice t)
-    tm::Operands op;
-    tm::make_operands(boxes, sx, sy, sz, MU, &op);
-    {
-        auto cen = [](int d) { return (d & 0xFFFFFF) | (((d >> 24) & 1) << 28); };
-        auto nxt = [](int d) { return (d & 0xFFFFFF) | (2 << 28); };
-        op.own = cen(op.own);
+    // ---- consumer side: operand descriptors (tile independent; tm::make_descriptors, tabulated once on the host)
+    int od[tm::NDESC];
 #pragma unroll
-        for (int jj = 0; jj < 3; jj++) {
-            const int nu = tm::staple_dir(MU, jj);
-            op.up[jj][0] = cen(op.up[jj][0]);
-            op.up[jj][1] = (MU < 3 && nu == 3) ? nxt(op.up[jj][1]) : cen(op.up[jj][1]);
-            op.up[jj][2] = (MU == 3) ? nxt(op.up[jj][2]) : cen(op.up[jj][2]);
-            if (nu < 3) {
-                op.dn[jj][0] = cen(op.dn[jj][0]);
-                op.dn[jj][1] = cen(op.dn[jj][1]);
-                op.dn[jj][2] = (MU == 3) ? nxt(op.dn[jj][2]) : cen(op.dn[jj][2]);
-            }
-        }
-    }
+    for (int i = 0; i < tm::NDESC; i++) od[i] = tab->desc[i][tid];
 
     // ---- producer side: lane b of warp 0 owns box b (31 boxes per slice)
     const bool is_producer = tid < tm::NBOX;
     int bx_o[3] = {0, 0, 0}, b_lam = 0, b_isr = 0, b_base = 0, b_shape = 0;
     if (is_producer) {
-        const tm::Box bb = boxes[tid];
-        bx_o[0] = bb.o[0]; bx_o[1] = bb.o[1]; bx_o[2] = bb.o[2];
-        b_lam = bb.lam; b_isr = bb.is_r; b_base = bb.base;
-        b_shape = tm::shape_index(bb.e[0], bb.e[1], bb.e[2]);
+        bx_o[0] = tab->box[tid][0]; bx_o[1] = tab->box[tid][1]; bx_o[2] = tab->box[tid][2];
+        b_lam = tab->box[tid][3]; b_isr = tab->box[tid][4]; b_base = tab->box[tid][5]; b_shape = tab->box[tid][6];
     }
     uint64_t* const barS = bars;                 // [S_RING]
     uint64_t* const barR = bars + tm::S_RING;    // [R_RING]
@@ -321,41 +302,41 @@ __device__ __forceinline__ void tm_run(const int MU, const TmMaps& maps, const G
 #if GFB_TM_DEBUG == 1
 #pragma unroll
             for (int jj = 0; jj < 3; jj++) {
-                m3_add(V, lds_m3(at(op.up[jj][0]))); m3_add(V, lds_m3(at(op.up[jj][1]))); m3_add(V, lds_m3(at(op.up[jj][2])));
-                if (jj < 2 || MU == 3) { m3_add(V, lds_m3(at(op.dn[jj][0]))); m3_add(V, lds_m3(at(op.dn[jj][1]))); m3_add(V, lds_m3(at(op.dn[jj][2]))); }
+                m3_add(V, lds_m3(at(od[1 + 6 * jj]))); m3_add(V, lds_m3(at(od[2 + 6 * jj]))); m3_add(V, lds_m3(at(od[3 + 6 * jj])));
+                if (jj < 2 || MU == 3) { m3_add(V, lds_m3(at(od[4 + 6 * jj]))); m3_add(V, lds_m3(at(od[5 + 6 * jj]))); m3_add(V, lds_m3(at(od[6 + 6 * jj]))); }
             }
-            U = lds_m3(at(op.own));
+            U = lds_m3(at(od[0]));
 #else
             auto upper = [&](int jj) {  // A B C^dag
-                const R2 A = lds_rows01(at(op.up[jj][0]));
-                const M3 B = lds_m3(at(op.up[jj][1]));
+                const R2 A = lds_rows01(at(od[1 + 6 * jj]));
+                const M3 B = lds_m3(at(od[2 + 6 * jj]));
                 const R2 T = r2_mul_nn(A, B);
-                const M3 C = lds_m3(at(op.up[jj][2]));
+                const M3 C = lds_m3(at(od[3 + 6 * jj]));
                 acc_su3(V, r2_mul_nd(T, C));
             };
             auto lower = [&](int jj) {  // A^dag B C
-                const R2 A = lds_dag_rows01(at(op.dn[jj][0]));
-                const M3 B = lds_m3(at(op.dn[jj][1]));
+                const R2 A = lds_dag_rows01(at(od[4 + 6 * jj]));
+                const M3 B = lds_m3(at(od[5 + 6 * jj]));
                 const R2 T = r2_mul_nn(A, B);
-                const M3 C = lds_m3(at(op.dn[jj][2]));
+                const M3 C = lds_m3(at(od[6 + 6 * jj]));
                 acc_su3(V, r2_mul_nn(T, C));
             };
             upper(0); lower(0);
             upper(1); lower(1);
             if (MU == 3) {
                 upper(2); lower(2);
-                U = lds_m3(at(op.own));
+                U = lds_m3(at(od[0]));
             } else {
                 // nu = t: the upper staple U_t(x) U_mu(x+t) U_t(x+mu)^dag and the NEXT slice's backward staple
                 // U_t(x)^dag U_mu(x) U_t(x+mu) share A = U_t(x) and C = U_t(x+mu); B of the latter is the own link
-                const M3 A = lds_m3(at(op.up[2][0]));
-                const M3 C = lds_m3(at(op.up[2][2]));
+                const M3 A = lds_m3(at(od[13]));
+                const M3 C = lds_m3(at(od[15]));
                 {
-                    const M3 B = lds_m3(at(op.up[2][1]));
+                    const M3 B = lds_m3(at(od[14]));
                     const R2 T = r2_mul_nn(rows01(A), B);
                     acc_su3(V, r2_mul_nd(T, C));
                 }
-                U = lds_m3(at(op.own));
+                U = lds_m3(at(od[0]));
                 const R2 T = r2_mul_nn(rows01_dag(A), U);
                 G = r2_mul_nn(T, C);
             }
@@ -393,26 +374,23 @@ __device__ __forceinline__ void tm_run(const int MU, const TmMaps& maps, const G
 }
 
 constexpr size_t kTmBarOff = tm::SMEM_DATA;
-constexpr size_t kTmBoxOff = kTmBarOff + 8 * (tm::S_RING + tm::R_RING);
 
 template <bool READ_Z, bool WRITE_Z, bool DO_EXP>
 __global__ void __launch_bounds__(tm::NTHREADS, 1)
-k_tmarch_fused(const __grid_constant__ TmMaps maps, Geom g, TmPlan pl, const double2* __restrict__ uin, double2* __restrict__ uout,
+k_tmarch_fused(const __grid_constant__ TmMaps maps, const tm::Tables* __restrict__ tab, Geom g, TmPlan pl, const double2* __restrict__ uin, double2* __restrict__ uout,
                const double* __restrict__ zin, double* __restrict__ zout, double a, double b, double c) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + kTmBarOff);
-    tm::Box* const boxes = reinterpret_cast<tm::Box*>(smem + kTmBoxOff);
     if (threadIdx.x == 0) {
-        tm::make_boxes(boxes);
         for (int i = 0; i < tm::S_RING + tm::R_RING; i++) mbar_init(bars + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     const int mu = threadIdx.x / tm::SITES;  // warp-uniform: two warps per direction
-    tm_run<READ_Z, WRITE_Z, DO_EXP>(mu, maps, g, pl, uin, uout, zin, zout, a, b, c, smem, bars, boxes);
+    tm_run<READ_Z, WRITE_Z, DO_EXP>(mu, maps, g, pl, uin, uout, zin, zout, a, b, c, smem, bars, tab);
 }
 
-constexpr size_t kTmSmem = kTmBoxOff + tm::NBOX * sizeof(tm::Box);
+constexpr size_t kTmSmem = kTmBarOff + 8 * (tm::S_RING + tm::R_RING);
 
 // t-segments: enough (segment, tile) items to fill the SMs evenly, as few segment prologues as possible
 TmPlan make_plan(const Geom& g, int t_begin, int t_count, int nsm) {
@@ -434,6 +412,22 @@ TmPlan make_plan(const Geom& g, int t_begin, int t_count, int nsm) {
     pl.seg_len = (t_count + best_nseg - 1) / best_nseg;
     pl.nseg = (t_count + pl.seg_len - 1) / pl.seg_len;
     return pl;
+}
+
+// geometry tables in device memory, one copy per device
+const tm::Tables* device_tables(int dev) {
+    static std::mutex mtx;
+    static const tm::Tables* per_dev[64] = {};
+    std::lock_guard<std::mutex> lock(mtx);
+    if (per_dev[dev & 63]) return per_dev[dev & 63];
+    static tm::Tables host;
+    static bool built = false;
+    if (!built) { tm::make_tables(&host); built = true; }
+    tm::Tables* d = nullptr;
+    if (cudaMalloc(&d, sizeof(tm::Tables)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaMemcpy(d, &host, sizeof(tm::Tables), cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); cudaFree(d); return nullptr; }
+    per_dev[dev & 63] = d;
+    return d;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -492,33 +486,43 @@ bool launch_tmarch_fused(cudaStream_t st, const Geom& g, int t_begin, int t_coun
     if (g.t_stride != 1 || t_count < 2) return false;
     if (g.nx % tm::BX || g.ny % tm::BY || g.nz % tm::BZ) return false;
     if (uout == uin) return false;
+    int dev = 0;
+    cudaGetDevice(&dev);
     static int nsm = 0;
-    if (nsm == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    }
-    TmPlan pl = make_plan(g, t_begin, t_count, nsm);
+    if (nsm == 0) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    // Multi-GPU slabs: a persistent grid fills every SM for the whole pass (231 KB of shared memory, 255 registers per thread), so
+    // NCCL's send/recv kernels of the overlapped halo exchange could not start before it ends (measured: 7.5 ms instead of 5.2 ms
+    // per 64^4/2 step).  There the grid is one CTA per (tile, segment) item instead: SMs free up every item and the high-priority
+    // halo stream gets them first.  GFB200_TMARCH_RESERVE_SMS=n additionally keeps n SMs out of the plan.
+    const bool slab = g.nslots > g.tloc;
+    int reserve = 0;
+    if (const char* er = getenv("GFB200_TMARCH_RESERVE_SMS")) reserve = atoi(er);
+    if (reserve < 0 || reserve >= nsm) reserve = 0;
+    int persistent = slab ? 0 : 1;
+    if (const char* ep = getenv("GFB200_TMARCH_PERSISTENT")) persistent = atoi(ep);
+    const int nsm_use = nsm - reserve;
+    TmPlan pl = make_plan(g, t_begin, t_count, nsm_use);
     if (const char* e = getenv("GFB200_TMARCH_SEGLEN")) {  // test hook: force the t-segment length
         const int len = atoi(e);
         if (len >= 1) { pl.seg_len = len < t_count ? len : t_count; pl.nseg = (t_count + pl.seg_len - 1) / pl.seg_len; }
     }
     const TmMaps* maps = tensor_maps_for(uin, g);
-    if (!maps) return false;
+    const tm::Tables* tab = device_tables(dev);
+    if (!maps || !tab) return false;
     const long nitems = (long)pl.ntiles * pl.nseg;
-    const unsigned grid = (unsigned)(nitems < nsm ? nitems : nsm);
+    const unsigned grid = (unsigned)((!persistent || nitems < nsm_use) ? nitems : nsm_use);
 #define GFB_LAUNCH_TM(R, W, E)                                                                                                  \
     do {                                                                                                                        \
         auto kern = k_tmarch_fused<R, W, E>;                                                                                    \
-        static bool attr_set = false;                                                                                           \
-        if (!attr_set) {                                                                                                        \
+        static bool attr_set[64] = {};  /* per device: one process may drive several GPUs */                                    \
+        if (!attr_set[dev & 63]) {                                                                                              \
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmSmem) != cudaSuccess) {         \
                 cudaGetLastError();                                                                                             \
                 return false;                                                                                                   \
             }                                                                                                                   \
-            attr_set = true;                                                                                                    \
+            attr_set[dev & 63] = true;                                                                                          \
         }                                                                                                                       \
-        kern<<<grid, tm::NTHREADS, kTmSmem, st>>>(*maps, g, pl, uin, uout, zin, zout, fa.a, fa.b, fa.c);                                \
+        kern<<<grid, tm::NTHREADS, kTmSmem, st>>>(*maps, tab, g, pl, uin, uout, zin, zout, fa.a, fa.b, fa.c);                                \
     } while (0)
     if (fa.read_z) {
         if (fa.do_exp) GFB_LAUNCH_TM(true, true, true);

@@ -170,5 +170,48 @@ TM_HD void make_operands(const Box* b, int sx, int sy, int sz, int mu, Operands*
     }
 }
 
+// Final per-thread operand descriptors of the kernel, in the order the hot loop uses them:
+//   d[0] own link;  d[1+6j .. 6+6j] = up A,B,C, dn A,B,C of iteration j (dn of the nu = t iteration of a spatial link: unused, 0)
+//   bits 0-15 byte offset, 16-23 box volume, bit 28: R part of slice t, bit 29: S part of slice t+1 (neither: S part of slice t)
+constexpr int NDESC = 19;
+TM_HD void make_descriptors(const Box* b, int sx, int sy, int sz, int mu, int* d) {
+    Operands op;
+    make_operands(b, sx, sy, sz, mu, &op);
+    d[0] = (op.own & 0xFFFFFF) | (((op.own >> 24) & 1) << 28);
+    for (int j = 0; j < 3; j++) {
+        const int nu = staple_dir(mu, j);
+        for (int o = 0; o < 3; o++) {
+            // a +t shift moves the operand to slice t+1: B of the upper staple when nu = t, C of both staples when mu = t
+            const bool next_up = (o == 1 && mu < 3 && nu == 3) || (o == 2 && mu == 3);
+            const bool next_dn = (o == 2 && mu == 3);
+            const int u = op.up[j][o], l = op.dn[j][o];
+            d[1 + 6 * j + o] = next_up ? ((u & 0xFFFFFF) | (2 << 28)) : ((u & 0xFFFFFF) | (((u >> 24) & 1) << 28));
+            d[4 + 6 * j + o] = (nu == 3) ? 0 : (next_dn ? ((l & 0xFFFFFF) | (2 << 28)) : ((l & 0xFFFFFF) | (((l >> 24) & 1) << 28)));
+        }
+    }
+}
+
+// what the kernel reads at start-up instead of recomputing the geometry per CTA (built once on the host)
+struct Tables {
+    int desc[NDESC][NTHREADS];  // [i][thread]: coalesced
+    int box[NBOX][8];           // o0, o1, o2, lam, is_r, base, shape, volume
+};
+inline void make_tables(Tables* t) {
+    Box b[NBOX];
+    make_boxes(b);
+    for (int tid = 0; tid < NTHREADS; tid++) {
+        const int mu = tid / SITES, sidx = tid % SITES;
+        int d[NDESC];
+        make_descriptors(b, sidx % BX, (sidx / BX) % BY, sidx / (BX * BY), mu, d);
+        for (int i = 0; i < NDESC; i++) t->desc[i][tid] = d[i];
+    }
+    for (int i = 0; i < NBOX; i++) {
+        t->box[i][0] = b[i].o[0]; t->box[i][1] = b[i].o[1]; t->box[i][2] = b[i].o[2];
+        t->box[i][3] = b[i].lam; t->box[i][4] = b[i].is_r; t->box[i][5] = b[i].base;
+        t->box[i][6] = shape_index(b[i].e[0], b[i].e[1], b[i].e[2]);
+        t->box[i][7] = box_volume(b[i]);
+    }
+}
+
 }  // namespace tm
 }  // namespace gfb

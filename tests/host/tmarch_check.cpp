@@ -80,42 +80,36 @@ int main(int argc, char** argv) {
                 }
                 return id;
             };
-            auto cen = [&](int d) { if (d < 0) { printf("missing operand\n"); exit(1); } return ((d >> 24) & 1) ? fetch(R, (size_t)(j & 1) * R_BYTES / 16, d) : fetch(S, (size_t)rs * S_BYTES / 16, d); };
-            auto nxt = [&](int d) { if (d < 0 || ((d >> 24) & 1)) { printf("next-slice operand not in S\n"); exit(1); } return fetch(S, (size_t)rs1 * S_BYTES / 16, d); };
+            // final descriptors (tm::make_descriptors): bit 28 = R part of slice t, bit 29 = S part of slice t+1
+            auto rd = [&](int d) {
+                if ((d >> 29) & 1) return fetch(S, (size_t)rs1 * S_BYTES / 16, d);
+                if ((d >> 28) & 1) return fetch(R, (size_t)(j & 1) * R_BYTES / 16, d);
+                return fetch(S, (size_t)rs * S_BYTES / 16, d);
+            };
             for (int mu = 0; mu < 4; mu++) for (int sz = 0; sz < BZ; sz++) for (int sy = 0; sy < BY; sy++) for (int sx = 0; sx < BX; sx++) {
-                Operands op;
-                make_operands(boxes, sx, sy, sz, mu, &op);
+                int d[NDESC];
+                make_descriptors(boxes, sx, sy, sz, mu, d);
                 const int X = x0 + sx, Y = y0 + sy, Z = z0 + sz;
                 int e[4][4] = {{1,0,0,0},{0,1,0,0},{0,0,1,0},{0,0,0,1}};
                 auto id = [&](int lam, int dplus, int dminus) {
                     int p[4] = {X, Y, Z, t};
-                    if (dplus >= 0) for (int d = 0; d < 4; d++) p[d] += e[dplus][d];
-                    if (dminus >= 0) for (int d = 0; d < 4; d++) p[d] -= e[dminus][d];
+                    if (dplus >= 0) for (int q = 0; q < 4; q++) p[q] += e[dplus][q];
+                    if (dminus >= 0) for (int q = 0; q < 4; q++) p[q] -= e[dminus][q];
                     return link_id(lam, p[0], p[1], p[2], p[3]);
                 };
 #define EXPECT(got, want, what) do { if ((got) != (want)) { printf("mismatch %s mu=%d site=%d,%d,%d t=%d tile=%d,%d,%d got %ld want %ld\n", what, mu, sx, sy, sz, t, x0, y0, z0, (long)(got), (long)(want)); return 1; } checked++; } while (0)
-                EXPECT(cen(op.own), id(mu, -1, -1), "own");
+                EXPECT(rd(d[0]), id(mu, -1, -1), "own");
                 for (int jj = 0; jj < 3; jj++) {
                     const int nu = staple_dir(mu, jj);
-                    if (mu < 3 && nu < 3) {
-                        EXPECT(cen(op.up[jj][0]), id(nu, -1, -1), "upA");
-                        EXPECT(cen(op.up[jj][1]), id(mu, nu, -1), "upB");
-                        EXPECT(cen(op.up[jj][2]), id(nu, mu, -1), "upC");
-                        EXPECT(cen(op.dn[jj][0]), id(nu, -1, nu), "dnA");
-                        EXPECT(cen(op.dn[jj][1]), id(mu, -1, nu), "dnB");
-                        EXPECT(cen(op.dn[jj][2]), id(nu, mu, nu), "dnC");
-                    } else if (mu < 3) {
-                        EXPECT(cen(op.up[jj][0]), id(3, -1, -1), "tA");
-                        EXPECT(nxt(op.up[jj][1]), id(mu, 3, -1), "tB");
-                        EXPECT(cen(op.up[jj][2]), id(3, mu, -1), "tC");
-                    } else {
-                        EXPECT(cen(op.up[jj][0]), id(nu, -1, -1), "3upA");
-                        EXPECT(cen(op.up[jj][1]), id(3, nu, -1), "3upB");
-                        EXPECT(nxt(op.up[jj][2]), id(nu, 3, -1), "3upC");
-                        EXPECT(cen(op.dn[jj][0]), id(nu, -1, nu), "3dnA");
-                        EXPECT(cen(op.dn[jj][1]), id(3, -1, nu), "3dnB");
-                        EXPECT(nxt(op.dn[jj][2]), id(nu, 3, nu), "3dnC");
-                    }
+                    // upper staple  U_nu(x) U_mu(x+nu) U_nu(x+mu)^dag
+                    EXPECT(rd(d[1 + 6 * jj]), id(nu, -1, -1), "upA");
+                    EXPECT(rd(d[2 + 6 * jj]), id(mu, nu, -1), "upB");
+                    EXPECT(rd(d[3 + 6 * jj]), id(nu, mu, -1), "upC");
+                    if (nu < 3) {  // lower staple  U_nu(x-nu)^dag U_mu(x-nu) U_nu(x-nu+mu)
+                        EXPECT(rd(d[4 + 6 * jj]), id(nu, -1, nu), "dnA");
+                        EXPECT(rd(d[5 + 6 * jj]), id(mu, -1, nu), "dnB");
+                        EXPECT(rd(d[6 + 6 * jj]), id(nu, mu, nu), "dnC");
+                    } else if (jj != 2) { printf("nu = t must be the last iteration\n"); return 1; }
                 }
             }
             if (j + 1 < len) { copy_part(1, t + 1, (j + 1) & 1); copy_part(0, t + 2, rs2); }
