@@ -335,7 +335,7 @@ def main():
             },
             "roofline": {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": kern_bytes * sites_local,
-                         "note": "fp64 DFMA issue co-limits this kernel (about 1.6 kDFMA per link); see DESIGN.md section 3"},
+                         "note": "FP64 issue and shared-memory reads co-limit this kernel (about 1.5 k FP64 instructions and 141 LDS.128 per link); DESIGN.md section 3a, profiles/r1_tmarch.md"},
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,
             "gpu_launches": int(launches) * world,
