@@ -66,10 +66,7 @@ k_force_fused(Geom g, int t_begin, int t_count, const double2* __restrict__ uin,
     M3 s = staple_sum(uin, g, x, mu);
     const M3 umu = load_link(uin, g, x, mu);
     double z[8];
-    {
-        M3 w = mul_nd(umu, s);
-        ta_coeffs(w, z);
-    }
+    ta_coeffs_nd(umu, s, z);
     const unsigned zo = mom_offset(g, x, mu);
     const unsigned zsb = (unsigned)g.v3 * 8u;
 #pragma unroll

@@ -343,10 +343,7 @@ __device__ __forceinline__ void tm_run(const int MU, const TmMaps& maps, const G
 #endif
 
             double f[8];
-            {
-                const M3 w = mul_nd(U, V);
-                ta_coeffs(w, f);
-            }
+            ta_coeffs_nd(U, V, f);
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 double v = a * f[k];
