@@ -171,12 +171,12 @@ def test_md_reversibility(backend, oracle):
             assert np.abs(P.to_host() - Ph).max() < 2e-12
 
 
-def test_hmc_accept_reject_sequence(backend, oracle):
+@pytest.mark.parametrize("dims", [DIMS, (8, 4, 4, 4)])  # 4^4: k_force_fused; 8x4x4x4: the t-marching kernel
+def test_hmc_accept_reject_sequence(backend, oracle, dims):
     """20 trajectories of the docs/src/hmc.md:128-190 loop: identical accept/reject sequence, Delta H within 1e-9
     when each trajectory starts from the oracle's state (re-synchronised), and the free-running chain's sequence."""
     import gfb200
 
-    dims = DIMS
     beta, steps = 5.7, 20
     Uh = oracle.hot_start_philox(dims, 0x1234)
     # a few thermalisation flow steps put Delta H in the O(1) regime so accept and reject both occur
