@@ -690,20 +690,45 @@ int gfb_energy_density(gfb_gauge* g, int kind, double* out) {
 int gfb_polyakov(gfb_gauge* g, double* out2) {
     if (!g || !out2) return fail(g ? g->ctx : nullptr, GFB_ERR_ARG, "null argument");
     gfb_ctx* ctx = g->ctx;
-    if (ctx->nslabs_total != 1) return fail(ctx, GFB_ERR_ARG, "the Polyakov loop is implemented for a single t-slab only");
-    Slab& s = ctx->slabs[0];
-    Geom geo = geom_of(g, 0);
-    GFB_CHECK(ensure_partial(ctx, s, (size_t)plaquette_blocks(geo) * 2 + 16));
-    GFB_CUDA(ctx, cudaSetDevice(s.device));
-    int nb = 0;
-    launch_polyakov(s.stream, geo, g->d[0], s.d_partial, &nb);
-    launch_final_reduce(s.stream, s.d_partial, nb, s.d_result);
-    launch_final_reduce(s.stream, s.d_partial + nb, nb, s.d_result + 1);
-    GFB_CHECK(post_launch(ctx, 3));
+    const int G = ctx->nslabs_total;
+    const size_t v3 = (size_t)g->nx * g->ny * g->nz;
+    const size_t field = 9 * v3;  // double2 elements of one running-product field
+    // slab r continues the product of slabs 0..r-1 (handed over with NCCL send/recv) and the last slab takes the trace
+    for (int r = 0; r < G; r++) {
+        int li = -1, lprev = -1;
+        for (size_t i = 0; i < ctx->slabs.size(); i++) {
+            if (ctx->slabs[i].index == r) li = (int)i;
+            if (ctx->slabs[i].index == r - 1) lprev = (int)i;
+        }
+        if (li >= 0) GFB_CHECK(ensure_staging(ctx, ctx->slabs[li], 2 * field * sizeof(double2)));
+        if (r > 0 && (li >= 0 || lprev >= 0)) {
+            GFB_NCCL(ctx, ncclGroupStart());
+            if (lprev >= 0) {
+                Slab& sp = ctx->slabs[lprev];
+                GFB_NCCL(ctx, ncclSend(reinterpret_cast<double2*>(sp.d_staging) + field, field * 2, ncclDouble, r, sp.nccl, sp.stream));
+            }
+            if (li >= 0) {
+                Slab& sr = ctx->slabs[li];
+                GFB_NCCL(ctx, ncclRecv(sr.d_staging, field * 2, ncclDouble, r - 1, sr.nccl, sr.stream));
+            }
+            GFB_NCCL(ctx, ncclGroupEnd());
+        }
+        if (li < 0) continue;
+        Slab& s = ctx->slabs[li];
+        Geom geo = geom_of(g, li);
+        GFB_CHECK(ensure_partial(ctx, s, (size_t)plaquette_blocks(geo) * 2 + 16));
+        GFB_CUDA(ctx, cudaSetDevice(s.device));
+        double2* const stg = reinterpret_cast<double2*>(s.d_staging);
+        int nb = 0;
+        launch_polyakov(s.stream, geo, g->d[li], r > 0 ? stg : nullptr, r < G - 1 ? stg + field : nullptr, s.d_partial, &nb);
+        launch_final_reduce(s.stream, s.d_partial, nb, s.d_result);  // zero on every slab but the last
+        launch_final_reduce(s.stream, s.d_partial + nb, nb, s.d_result + 1);
+        GFB_CHECK(post_launch(ctx, 3));
+    }
     double v[2];
     GFB_CHECK(gather_scalars(ctx, 2, v));
-    out2[0] = v[0] / geo.v3;
-    out2[1] = v[1] / geo.v3;
+    out2[0] = v[0] / v3;
+    out2[1] = v[1] / v3;
     return GFB_OK;
 }
 

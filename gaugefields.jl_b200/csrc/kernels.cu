@@ -272,25 +272,31 @@ void launch_clover_energy(cudaStream_t st, const Geom& g, const double2* u, doub
 
 // Polyakov loop, single slab: one thread per spatial site multiplies U_t along t
 // (calculate_Polyakov_loop, AbstractGaugefields.jl:2929-2956).  partial[b] = Re, partial[gridDim+b] = Im
-__global__ void __launch_bounds__(128) k_polyakov(Geom g, const double2* __restrict__ u, double* __restrict__ partial) {
+// pin  != null: continue the product of the previous slabs (9 planes of v3 elements);  pout != null: hand the running product
+// to the next slab instead of taking the trace (t-slabs multiply in slab order: the loop winds once around the global t extent)
+__global__ void __launch_bounds__(128) k_polyakov(Geom g, const double2* __restrict__ u, const double2* __restrict__ pin, double2* __restrict__ pout,
+                                                  double* __restrict__ partial) {
     const int s3 = blockIdx.x * blockDim.x + threadIdx.x;
     double re = 0.0, im = 0.0;
     if (s3 < g.v3) {
-        M3 p = m3_load(u + (size_t)(0 * 36 + 27) * g.v3 + s3, (unsigned)g.v3);
-        for (int t = 1; t < g.tloc; t++) {
+        M3 p = pin ? m3_load(pin + s3, (unsigned)g.v3) : m3_load(u + (size_t)(0 * 36 + 27) * g.v3 + s3, (unsigned)g.v3);
+        for (int t = pin ? 0 : 1; t < g.tloc; t++) {
             M3 q = m3_load(u + (size_t)(t * 36 + 27) * g.v3 + s3, (unsigned)g.v3);
             p = mul_nn(p, q);
         }
-        re = p.e[0].x + p.e[4].x + p.e[8].x;
-        im = p.e[0].y + p.e[4].y + p.e[8].y;
+        if (pout) m3_store(pout + s3, (unsigned)g.v3, p);
+        else {
+            re = p.e[0].x + p.e[4].x + p.e[8].x;
+            im = p.e[0].y + p.e[4].y + p.e[8].y;
+        }
     }
     double r = block_sum(re);
     double i = block_sum(im);
     if (threadIdx.x == 0) { partial[blockIdx.x] = r; partial[gridDim.x + blockIdx.x] = i; }
 }
-void launch_polyakov(cudaStream_t st, const Geom& g, const double2* u, double* partial, int* nblocks) {
+void launch_polyakov(cudaStream_t st, const Geom& g, const double2* u, const double2* pin, double2* pout, double* partial, int* nblocks) {
     int nb = (g.v3 + 127) / 128;
-    k_polyakov<<<nb, 128, 0, st>>>(g, u, partial);
+    k_polyakov<<<nb, 128, 0, st>>>(g, u, pin, pout, partial);
     *nblocks = nb;
 }
 

@@ -30,6 +30,7 @@ def main():
     assert np.array_equal(got, Uh[:, t0:t1])
     want = oracle.plaquette_sum(Uh, dims)
     assert abs(gfb200.calculate_Plaquette(U) - want) <= 1e-12 * abs(want) + 1e-12
+    assert abs(gfb200.measure_polyakov_loop(U, normalize=False) - oracle.polyakov(Uh, dims)) < 1e-13
     hot = gfb200.gauge_configuration(dims, backend=backend, start="hot", seed=1234).to_host(local=True)
     assert np.abs(hot - hot_ref[:, t0:t1]).max() < 1e-14
     loops = gfb200.make_loops_fromname("plaquette")

@@ -53,6 +53,8 @@ def test_two_slabs_match_oracle(backend2, oracle, dims):
     assert np.abs(F.to_host() - Fw).max() / np.abs(Fw).max() < 1e-12
     e = gfb200.energy_density(U)
     assert abs(e - oracle.energy_density_clover(Uh, dims)) < 1e-11 * max(1.0, abs(e))
+    # Polyakov loop: the running product is handed from slab to slab in t order
+    assert abs(gfb200.measure_polyakov_loop(U, normalize=False) - oracle.polyakov(Uh, dims)) < 1e-13
     for integ in (gfb200.QPQ, gfb200.PQP):
         for fused in (False, True):
             U.upload(Uh)
