@@ -134,11 +134,18 @@ static int gather_scalars(gfb_ctx* ctx, int nslots, double* out) {
 // overlapped = true : on the high-priority halo streams, after the work already queued on the compute streams (the
 //   boundary time-slices); ev_b marks completion and the caller makes the compute stream wait on it only AFTER it has
 //   queued the interior slices, so the exchange over NVLink runs concurrently with the interior compute.
-static int exchange_halo_buffers(gfb_ctx* ctx, const gfb_gauge* g, const std::vector<double2*>& buf, bool overlapped) {
+// su3 = true (the buffer holds unitary links: outputs of the fused update passes): only rows 0 and 1 of every link travel
+//   (planes k = 0..5 of each direction are contiguous in the slice) and the receiver rebuilds row 2 = conj(row0 x row1) on the
+//   halo stream: 42 instead of 63 planes per step.  With 8 slices per GPU the exchange, not the interior compute, sets the step
+//   time (profiles/r1_tmarch.md), so the bytes matter.
+static int exchange_halo_buffers(gfb_ctx* ctx, const gfb_gauge* g, const std::vector<double2*>& buf, bool overlapped, bool su3 = false) {
     const int G = ctx->nslabs_total;
     if (G == 1) return GFB_OK;
+    static const bool allow_su3 = [] { const char* e = getenv("GFB200_HALO_SU3"); return e ? atoi(e) != 0 : true; }();
+    su3 = su3 && allow_su3;
+    const size_t v3 = (size_t)g->nx * g->ny * g->nz;
     const size_t slice = g->slice_elems() * 2;  // doubles
-    const size_t up_count = (size_t)27 * g->nx * g->ny * g->nz * 2;  // the t+1 halo only needs the three spatial links
+    const size_t up_count = (size_t)27 * v3 * 2;  // the t+1 halo only needs the three spatial links
     if (overlapped) {
         for (auto& s : ctx->slabs) {
             GFB_CUDA(ctx, cudaSetDevice(s.device));
@@ -156,12 +163,29 @@ static int exchange_halo_buffers(gfb_ctx* ctx, const gfb_gauge* g, const std::ve
         double* last = base + (size_t)(g->tloc - 1) * slice;
         double* up = base + (size_t)g->tloc * slice;
         double* dn = base + (size_t)(g->tloc + 1) * slice;
-        GFB_NCCL(ctx, ncclSend(first, up_count, ncclDouble, prev, s.nccl, st));
-        GFB_NCCL(ctx, ncclSend(last, slice, ncclDouble, next, s.nccl, st));
-        GFB_NCCL(ctx, ncclRecv(up, up_count, ncclDouble, next, s.nccl, st));
-        GFB_NCCL(ctx, ncclRecv(dn, slice, ncclDouble, prev, s.nccl, st));
+        if (!su3) {
+            GFB_NCCL(ctx, ncclSend(first, up_count, ncclDouble, prev, s.nccl, st));
+            GFB_NCCL(ctx, ncclSend(last, slice, ncclDouble, next, s.nccl, st));
+            GFB_NCCL(ctx, ncclRecv(up, up_count, ncclDouble, next, s.nccl, st));
+            GFB_NCCL(ctx, ncclRecv(dn, slice, ncclDouble, prev, s.nccl, st));
+        } else {
+            const size_t dir = 9 * v3 * 2, rows01 = 6 * v3 * 2;  // doubles per direction / per two rows of a direction
+            for (int mu = 0; mu < 3; mu++) GFB_NCCL(ctx, ncclSend(first + mu * dir, rows01, ncclDouble, prev, s.nccl, st));
+            for (int mu = 0; mu < 4; mu++) GFB_NCCL(ctx, ncclSend(last + mu * dir, rows01, ncclDouble, next, s.nccl, st));
+            for (int mu = 0; mu < 3; mu++) GFB_NCCL(ctx, ncclRecv(up + mu * dir, rows01, ncclDouble, next, s.nccl, st));
+            for (int mu = 0; mu < 4; mu++) GFB_NCCL(ctx, ncclRecv(dn + mu * dir, rows01, ncclDouble, prev, s.nccl, st));
+        }
     }
     GFB_NCCL(ctx, ncclGroupEnd());
+    if (su3) {
+        for (size_t i = 0; i < ctx->slabs.size(); i++) {
+            Slab& s = ctx->slabs[i];
+            GFB_CUDA(ctx, cudaSetDevice(s.device));
+            launch_complete_su3_rows(overlapped ? s.comm_stream : s.stream, make_geom(ctx, g->nx, g->ny, g->nz, g->nt, s.index), buf[i]);
+            ctx->launches += 1;
+            GFB_CUDA(ctx, cudaGetLastError());
+        }
+    }
     if (overlapped) {
         for (auto& s : ctx->slabs) {
             GFB_CUDA(ctx, cudaSetDevice(s.device));
@@ -754,7 +778,7 @@ static int fused_pass(gfb_gauge* g, const std::vector<double2*>& uin, const std:
         return GFB_OK;
     }
     for (size_t i = 0; i < ctx->slabs.size(); i++) GFB_CHECK(launch(i, 0, 2, g->tloc - 1));  // slices 0 and tloc-1 in one launch
-    GFB_CHECK(exchange_halo_buffers(ctx, g, *uout, true));
+    GFB_CHECK(exchange_halo_buffers(ctx, g, *uout, true, true));  // unitary links: two rows travel
     for (size_t i = 0; i < ctx->slabs.size(); i++) GFB_CHECK(launch(i, 1, g->tloc - 2));
     return join_halo_exchange(ctx);
 }
@@ -811,7 +835,7 @@ int gfb_update_links(gfb_gauge* g, const gfb_mom* p, double eps) {
     // site-local update: boundary slices first, their exchange overlaps the interior (set_wing_U!/set_halo! of the
     // reference happens inside substitute_U!, gaugefields_4D_MPILattice.jl:497-512)
     for (size_t i = 0; i < ctx->slabs.size(); i++) GFB_CHECK(launch(i, 0, 2, g->tloc - 1));
-    GFB_CHECK(exchange_halo_buffers(ctx, g, g->d, true));
+    GFB_CHECK(exchange_halo_buffers(ctx, g, g->d, true, true));
     for (size_t i = 0; i < ctx->slabs.size(); i++) GFB_CHECK(launch(i, 1, g->tloc - 2));
     GFB_CHECK(join_halo_exchange(ctx));
     g->halo_valid = true;

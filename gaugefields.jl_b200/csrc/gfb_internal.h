@@ -133,6 +133,8 @@ void launch_set_cold(cudaStream_t st, const Geom& g, double2* u);
 void launch_set_hot(cudaStream_t st, const Geom& g, double2* u, unsigned long long seed);
 void launch_gaussian(cudaStream_t st, const Geom& g, double* p, unsigned long long seed, unsigned long long sweep, double sigma);
 void launch_reunitarize(cudaStream_t st, const Geom& g, double2* u);
+// rebuilds row 2 = conj(row0 x row1) of the links in the two halo slots (3 spatial directions in the t+1 slot, 4 in the t-1 slot)
+void launch_complete_su3_rows(cudaStream_t st, const Geom& g, double2* u);
 void launch_axpy(cudaStream_t st, double* y, double a, const double* x, size_t n);
 void launch_staple_field(cudaStream_t st, const Geom& g, const double2* u, double2* out, double scale);
 void launch_kick_from_dsdu(cudaStream_t st, const Geom& g, const double2* u, const double2* d, double* p, double factor);

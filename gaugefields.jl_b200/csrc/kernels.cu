@@ -300,6 +300,30 @@ void launch_polyakov(cudaStream_t st, const Geom& g, const double2* u, const dou
     *nblocks = nb;
 }
 
+// halo slots after a two-row exchange of unitary links: row 2 = conj(row0 x row1) (the identity reunitarize() ends with)
+__global__ void __launch_bounds__(256) k_complete_su3_rows(Geom g, double2* __restrict__ u) {
+    const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long per_dir = g.v3;
+    if (n >= 7 * per_dir) return;
+    const int d = (int)(n / per_dir);  // 0..2: t+1 slot, directions 0..2;  3..6: t-1 slot, directions 0..3
+    const int s3 = (int)(n - (long)d * per_dir);
+    const int slot = d < 3 ? g.tloc : g.tloc + 1;
+    const int mu = d < 3 ? d : d - 3;
+    double2* p = u + (size_t)(slot * 36 + mu * 9) * g.v3 + s3;
+    double2 r[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) r[k] = p[(size_t)k * g.v3];
+    double2 t;
+    t = cmul(r[1], r[5]); { double2 v = cmul(r[2], r[4]); t.x -= v.x; t.y -= v.y; } p[(size_t)6 * g.v3] = make_double2(t.x, -t.y);
+    t = cmul(r[2], r[3]); { double2 v = cmul(r[0], r[5]); t.x -= v.x; t.y -= v.y; } p[(size_t)7 * g.v3] = make_double2(t.x, -t.y);
+    t = cmul(r[0], r[4]); { double2 v = cmul(r[1], r[3]); t.x -= v.x; t.y -= v.y; } p[(size_t)8 * g.v3] = make_double2(t.x, -t.y);
+}
+void launch_complete_su3_rows(cudaStream_t st, const Geom& g, double2* u) {
+    if (g.nslots <= g.tloc) return;
+    const long n = 7L * g.v3;
+    k_complete_su3_rows<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, u);
+}
+
 // ------------------------------------------------------------------------------------------------
 // host layout <-> device layout.  staging holds this slab's chunk of the reference's gathered array
 // ComplexF64[3,3,NX,NY,NZ,T] (element (i,j) of a site at i + 3j; src/API.jl:516-529)
