@@ -136,12 +136,13 @@ static int gather_scalars(gfb_ctx* ctx, int nslots, double* out) {
 //   queued the interior slices, so the exchange over NVLink runs concurrently with the interior compute.
 // su3 = true (the buffer holds unitary links: outputs of the fused update passes): only rows 0 and 1 of every link travel
 //   (planes k = 0..5 of each direction are contiguous in the slice) and the receiver rebuilds row 2 = conj(row0 x row1) on the
-//   halo stream: 42 instead of 63 planes per step.  With 8 slices per GPU the exchange, not the interior compute, sets the step
-//   time (profiles/r1_tmarch.md), so the bytes matter.
+//   halo stream: 42 instead of 63 planes per step.  Opt-in (GFB200_HALO_SU3=1): measured +3 % at 64^4 on 2 GPUs with 8 slices
+//   each but -7 % on 8 GPUs (14 instead of 4 NCCL operations per step and one more kernel; the 8-GPU step is not
+//   bandwidth-bound) -- profiles/r1_tmarch.md.
 static int exchange_halo_buffers(gfb_ctx* ctx, const gfb_gauge* g, const std::vector<double2*>& buf, bool overlapped, bool su3 = false) {
     const int G = ctx->nslabs_total;
     if (G == 1) return GFB_OK;
-    static const bool allow_su3 = [] { const char* e = getenv("GFB200_HALO_SU3"); return e ? atoi(e) != 0 : true; }();
+    static const bool allow_su3 = [] { const char* e = getenv("GFB200_HALO_SU3"); return e ? atoi(e) != 0 : false; }();
     su3 = su3 && allow_su3;
     const size_t v3 = (size_t)g->nx * g->ny * g->nz;
     const size_t slice = g->slice_elems() * 2;  // doubles
