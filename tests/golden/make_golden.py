@@ -1,5 +1,6 @@
-"""Generates tests/golden/wilson_4x4x4x4.npz -- known-answer vectors for the hot path on the reference's own test
-lattice (4^4, SU(3), Wilson beta = 5.7: test/HMC_test.jl scale, BASELINE.json configs[0]).
+"""Generates tests/golden/wilson_4x4x4x4.npz and wilson_8x4x2x4.npz -- known-answer vectors for the hot path on the reference's
+own test lattice (4^4, SU(3), Wilson beta = 5.7: test/HMC_test.jl scale, BASELINE.json configs[0]) and on a lattice of the same
+volume that the 8x4x2 tile of the t-marching kernel divides (4^4 runs in k_force_fused, 8x4x2x4 in k_tmarch_fused).
 
 The reference cannot run in the build image (Julia + un-vendored LatticeMatrices.jl), so these vectors come from the CPU
 oracle (oracle/gf_oracle.cpp), which is itself pinned to the reference's golden values in tests/test_oracle_pins.py; two of
@@ -17,11 +18,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "..", "..", "oracle"))
 import gf_oracle as oracle  # noqa: E402
 
-DIMS = (4, 4, 4, 4)
 BETA = 5.7
 
 
-def main():
+def make(DIMS):
     out = {}
     U = oracle.hot_start_philox(DIMS, 1234)
     P = oracle.gaussian_momenta(DIMS, 0x5678, 0)
@@ -55,16 +55,19 @@ def main():
     d0 = oracle.stout_backward(oracle.stout_backward(oracle.wilson_dSdU(U2, DIMS, BETA), U1, DIMS, 0.1), U, DIMS, 0.1)
     out["stout_force"] = oracle.kick_from_dSdU(oracle.new_p(DIMS), U, d0, DIMS, -1.0 / 3.0)
     # the reference's own golden values (test/init.jl:276-283, test/gradientflow_test.jl:129-139)
-    Us = oracle.hot_start_stable123(DIMS)
-    out["ref_hot_plaquette"] = np.float64(0.008449494077606137)
-    out["oracle_hot_plaquette"] = oracle.plaquette(Us, DIMS)
-    for _ in range(100):
-        oracle.flow_step(Us, DIMS, 0.01)
-    out["ref_flow_plaquette"] = np.float64(0.8786515255315753)
-    out["oracle_flow_plaquette"] = oracle.plaquette(Us, DIMS)
-    np.savez_compressed(os.path.join(HERE, "wilson_4x4x4x4.npz"), **out)
-    print({k: (v.shape if hasattr(v, "shape") and v.shape else float(v)) for k, v in out.items()})
+    if DIMS == (4, 4, 4, 4):
+        Us = oracle.hot_start_stable123(DIMS)
+        out["ref_hot_plaquette"] = np.float64(0.008449494077606137)
+        out["oracle_hot_plaquette"] = oracle.plaquette(Us, DIMS)
+        for _ in range(100):
+            oracle.flow_step(Us, DIMS, 0.01)
+        out["ref_flow_plaquette"] = np.float64(0.8786515255315753)
+        out["oracle_flow_plaquette"] = oracle.plaquette(Us, DIMS)
+    name = "wilson_%s.npz" % "x".join(map(str, DIMS))
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, {k: (v.shape if hasattr(v, "shape") and v.shape else float(v)) for k, v in out.items()})
 
 
 if __name__ == "__main__":
-    main()
+    make((4, 4, 4, 4))
+    make((8, 4, 2, 4))
