@@ -5,7 +5,7 @@
 // Why (profiles/r1_ncu_force_fused.md): k_force_fused requests 19 link matrices per link through L1 (10.9 KB/site), 6.0 KB/site of
 // which come from L2 at the ~7 TB/s the L2->SM path delivers at 16 warps/SM; neither DRAM nor the FP64 pipe is the limit.
 // Here a CTA owns a spatial tile of 8x4x2 sites and marches along t.  Every link matrix the six-staple stencil of a slice needs is
-// copied into shared memory ONCE per tile and slice by TMA tensor copies (31 boxes per slice, one cp.async.bulk.tensor.4d each,
+// copied into shared memory ONCE per tile and slice by TMA tensor copies (21 boxes per slice, one cp.async.bulk.tensor.4d each,
 // issued by the lanes of warp 0, completion on mbarriers), one whole slice ahead of its use, so L2->SM traffic drops to 2.64
 // matrix loads per link (1.5 KB/site) and every operand is a fixed-latency LDS.128.  (The first version copied with per-thread
 // 16-byte cp.async: issuing 27 LDGSTS per thread and slice cost 24 % of the warp time -- profiles/r1_tmarch.md.)
@@ -49,7 +49,7 @@ struct R2 {
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 struct TmMaps {
-    CUtensorMap m[tm::NSHAPE];  // one per box shape: tensor = [plane][z][y][2*x doubles], box = 9 planes x ez x ey x 2*ex
+    CUtensorMap m[tm::NMAP];  // per box shape and number of merged directions: tensor = [plane][z][y][2*x doubles], box = 9*nlam planes x ez x ey x 2*ex
 };
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
@@ -205,7 +205,7 @@ __device__ __forceinline__ void tm_run(const int MU, const TmMaps& maps, const G
 #pragma unroll
     for (int i = 0; i < tm::NDESC; i++) od[i] = tab->desc[i][tid];
 
-    // ---- producer side: lane b of warp 0 owns box b (31 boxes per slice)
+    // ---- producer side: lane b of warp 0 owns box b (21 boxes per slice)
     const bool is_producer = tid < tm::NBOX;
     int bx_o[3] = {0, 0, 0}, b_lam = 0, b_isr = 0, b_base = 0, b_shape = 0;
     if (is_producer) {
@@ -459,10 +459,10 @@ const TmMaps* tensor_maps_for(const double2* u, const Geom& g) {
     const cuuint64_t gdim[4] = {(cuuint64_t)g.nx * 2, (cuuint64_t)g.ny, (cuuint64_t)g.nz, (cuuint64_t)g.nslots * 36};
     const cuuint64_t gstride[3] = {(cuuint64_t)g.nx * 16, (cuuint64_t)g.nx * g.ny * 16, (cuuint64_t)g.v3 * 16};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    for (int s = 0; s < tm::NSHAPE; s++) {
+    for (int s = 0; s < tm::NMAP; s++) {
         int e[3];
-        tm::shape_extent(s, e);
-        const cuuint32_t box[4] = {(cuuint32_t)e[0] * 2, (cuuint32_t)e[1], (cuuint32_t)e[2], 9};
+        tm::shape_extent(s / 3, e);
+        const cuuint32_t box[4] = {(cuuint32_t)e[0] * 2, (cuuint32_t)e[1], (cuuint32_t)e[2], (cuuint32_t)(9 * (s % 3 + 1))};
         if (encode(&maps.m[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double2*>(u), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return nullptr;

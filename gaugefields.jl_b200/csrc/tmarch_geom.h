@@ -13,8 +13,8 @@
 //   S part  (248 matrices)  spatial lam on the tile and on its -e_lam face                     [needed as t+1 AND as t]
 //   R part  (428 matrices)  everything else                                                    [needed only as t]
 // Ring depth: S 3 (t, t+1 and the t+2 being fetched), R 2 (t and the t+1 being fetched).
-// Every part is a list of BOXES (31 per slice), each fetched by one TMA tensor copy of 9 element planes
-// (cp.async.bulk.tensor.4d, box = 2*ex doubles x ey x ez x 9 planes); a box never crosses the periodic boundary because it is
+// Every part is a list of BOXES (21 per slice), each fetched by one TMA tensor copy of the 9 element planes of one to three
+// consecutive link directions (cp.async.bulk.tensor.4d, box = 2*ex doubles x ey x ez x 9*nlam planes); a box never crosses the periodic boundary because it is
 // either inside the tile's extent or a single halo layer in each direction, so its origin is wrapped per coordinate.
 // Inside a box the layout is the copy's: [k][z][y][x] 16-byte elements, i.e. element k of the matrix at box position i sits at
 // box_base + (k*n + i)*16 with n the box volume: the 8 x-consecutive lanes of an LDS.128 phase read 128 contiguous bytes.
@@ -35,16 +35,20 @@ constexpr int BX = 8, BY = 4, BZ = 2;
 constexpr int SITES = BX * BY * BZ;      // 64 sites, 256 link-threads
 constexpr int NTHREADS = 4 * SITES;
 constexpr int MAT_BYTES = 144;
-constexpr int NBOX = 31;
+constexpr int NBOX = 21;
 constexpr int NSHAPE = 7;
+constexpr int NMAP = 3 * NSHAPE;        // tensor maps: box shape x number of merged directions (1..3)
 constexpr int S_MATS = 248, R_MATS = 428;
 constexpr int S_BYTES = 35712;           // 248 matrices, every S box is a multiple of 8 matrices (no padding)
 constexpr int R_BYTES = 61952;           // 428 matrices + 320 bytes of padding (box bases are 128-byte aligned for TMA)
 constexpr int S_RING = 3, R_RING = 2;
 constexpr int SMEM_DATA = S_RING * S_BYTES + R_RING * R_BYTES;  // 231040
 
+// One TMA copy: the links of nlam consecutive directions lam .. lam+nlam-1 on a box of positions (their 9*nlam element planes
+// are contiguous in a slice, so directions that need the same positions share a copy: 21 copies per slice instead of 31).
+// Destination layout [plane][z][y][x]: direction lam+i occupies the sub-box at base + i*9*n*16, each sub-box is [k][pos].
 struct Box {
-    signed char lam, is_r;
+    signed char lam, nlam, is_r;
     signed char o[3];  // origin relative to the tile origin (-1 .. B)
     signed char e[3];  // extents
     int base;          // byte offset inside its part (128-byte aligned)
@@ -72,47 +76,49 @@ TM_HD void shape_extent(int s, int* e) {
 
 // Fills the NBOX boxes.  A box is described by the set of directions in which it is a halo layer:
 //   lo[d] = -1 / +1  -> the single layer at -1 / at B_d ;  0 -> the tile's extent in d
-TM_HD void put_box(Box* b, int* n, int* sbase, int* rbase, int lam, int is_r, int l0, int l1, int l2) {
+TM_HD void put_box(Box* b, int* n, int* sbase, int* rbase, int lam, int nlam, int is_r, int l0, int l1, int l2) {
     const int lo[3] = {l0, l1, l2};
     Box x;
-    x.lam = (signed char)lam; x.is_r = (signed char)is_r;
+    x.lam = (signed char)lam; x.nlam = (signed char)nlam; x.is_r = (signed char)is_r;
     for (int d = 0; d < 3; d++) {
         x.o[d] = (signed char)(lo[d] < 0 ? -1 : (lo[d] > 0 ? tile_extent(d) : 0));
         x.e[d] = (signed char)(lo[d] != 0 ? 1 : tile_extent(d));
     }
     int* base = is_r ? rbase : sbase;
     x.base = *base;
-    *base += pad128(box_volume(x) * MAT_BYTES);
+    *base += pad128(nlam * box_volume(x) * MAT_BYTES);
     b[(*n)++] = x;
+}
+// a face layer (sign sgn, direction i) in the R part for every link direction except `skip` (-1: none), merged into runs
+TM_HD void put_face_runs(Box* b, int* n, int* sbase, int* rbase, int i, int sgn, int skip) {
+    int l[3] = {0, 0, 0};
+    l[i] = sgn;
+    int lam = 0;
+    while (lam < 4) {
+        if (lam == skip) { lam++; continue; }
+        int run = 1;
+        while (lam + run < 4 && lam + run != skip) run++;
+        put_box(b, n, sbase, rbase, lam, run, 1, l[0], l[1], l[2]);
+        lam += run;
+    }
 }
 TM_HD int make_boxes(Box* b) {
     int n = 0, sbase = 0, rbase = 0;
-    for (int lam = 0; lam < 3; lam++) {  // S part: tile and the -e_lam layer
-        put_box(b, &n, &sbase, &rbase, lam, 0, 0, 0, 0);
-        put_box(b, &n, &sbase, &rbase, lam, 0, lam == 0 ? -1 : 0, lam == 1 ? -1 : 0, lam == 2 ? -1 : 0);
+    // S part: the three spatial directions on the tile (one copy), each one's -e_lam layer
+    put_box(b, &n, &sbase, &rbase, 0, 3, 0, 0, 0, 0);
+    for (int lam = 0; lam < 3; lam++) put_box(b, &n, &sbase, &rbase, lam, 1, 0, lam == 0 ? -1 : 0, lam == 1 ? -1 : 0, lam == 2 ? -1 : 0);
+    // R part: U_t on the tile
+    put_box(b, &n, &sbase, &rbase, 3, 1, 1, 0, 0, 0);
+    for (int i = 0; i < 3; i++) {
+        put_face_runs(b, &n, &sbase, &rbase, i, +1, i);  // +e_i face: every direction but i
+        put_face_runs(b, &n, &sbase, &rbase, i, -1, i);  // -e_i face: every direction but i (direction i's is the S layer)
     }
-    for (int lam = 0; lam < 3; lam++) {  // R part of a spatial direction
+    for (int lam = 0; lam < 3; lam++)                    // (+e_i, -e_lam) edges of a spatial direction
         for (int i = 0; i < 3; i++) {
             if (i == lam) continue;
             int l[3] = {0, 0, 0};
-            l[i] = +1;                     // +e_i face ...
-            put_box(b, &n, &sbase, &rbase, lam, 1, l[0], l[1], l[2]);
-            l[lam] = -1;                   // ... and its (+e_i, -e_lam) edge
-            put_box(b, &n, &sbase, &rbase, lam, 1, l[0], l[1], l[2]);
-        }
-        for (int i = 0; i < 3; i++) {
-            if (i == lam) continue;
-            int l[3] = {0, 0, 0};
-            l[i] = -1;                     // -e_i face
-            put_box(b, &n, &sbase, &rbase, lam, 1, l[0], l[1], l[2]);
-        }
-    }
-    put_box(b, &n, &sbase, &rbase, 3, 1, 0, 0, 0);  // U_t: tile and the six faces
-    for (int sgn = +1; sgn >= -1; sgn -= 2)
-        for (int i = 0; i < 3; i++) {
-            int l[3] = {0, 0, 0};
-            l[i] = sgn;
-            put_box(b, &n, &sbase, &rbase, 3, 1, l[0], l[1], l[2]);
+            l[i] = +1; l[lam] = -1;
+            put_box(b, &n, &sbase, &rbase, lam, 1, 1, l[0], l[1], l[2]);
         }
     return n;
 }
@@ -122,11 +128,12 @@ TM_HD int make_boxes(Box* b) {
 //   bit 24 set when the box belongs to the R part;  -1 when the position is not resident
 TM_HD int lookup(const Box* b, int lam, int x, int y, int z) {
     for (int i = 0; i < NBOX; i++) {
-        if (b[i].lam != lam) continue;
+        if (lam < b[i].lam || lam >= b[i].lam + b[i].nlam) continue;
         const int dx = x - b[i].o[0], dy = y - b[i].o[1], dz = z - b[i].o[2];
         if (dx < 0 || dy < 0 || dz < 0 || dx >= b[i].e[0] || dy >= b[i].e[1] || dz >= b[i].e[2]) continue;
         const int idx = dx + b[i].e[0] * (dy + b[i].e[1] * dz);
-        return (b[i].base + idx * 16) | (box_volume(b[i]) << 16) | ((b[i].is_r ? 1 : 0) << 24);
+        const int n = box_volume(b[i]);
+        return (b[i].base + (lam - b[i].lam) * 9 * n * 16 + idx * 16) | (n << 16) | ((b[i].is_r ? 1 : 0) << 24);
     }
     return -1;
 }
@@ -194,7 +201,7 @@ TM_HD void make_descriptors(const Box* b, int sx, int sy, int sz, int mu, int* d
 // what the kernel reads at start-up instead of recomputing the geometry per CTA (built once on the host)
 struct Tables {
     int desc[NDESC][NTHREADS];  // [i][thread]: coalesced
-    int box[NBOX][8];           // o0, o1, o2, lam, is_r, base, shape, volume
+    int box[NBOX][8];           // o0, o1, o2, first direction, is_r, base, tensor-map index, bytes
 };
 inline void make_tables(Tables* t) {
     Box b[NBOX];
@@ -208,8 +215,8 @@ inline void make_tables(Tables* t) {
     for (int i = 0; i < NBOX; i++) {
         t->box[i][0] = b[i].o[0]; t->box[i][1] = b[i].o[1]; t->box[i][2] = b[i].o[2];
         t->box[i][3] = b[i].lam; t->box[i][4] = b[i].is_r; t->box[i][5] = b[i].base;
-        t->box[i][6] = shape_index(b[i].e[0], b[i].e[1], b[i].e[2]);
-        t->box[i][7] = box_volume(b[i]);
+        t->box[i][6] = 3 * shape_index(b[i].e[0], b[i].e[1], b[i].e[2]) + (b[i].nlam - 1);
+        t->box[i][7] = b[i].nlam * box_volume(b[i]) * MAT_BYTES;
     }
 }
 

@@ -29,8 +29,9 @@ int main(int argc, char** argv) {
             const int n = box_volume(boxes[i]);
             int& base = boxes[i].is_r ? r : s;
             if (boxes[i].base != base || (base & 127)) { printf("box base %d\n", i); return 1; }
-            base += pad128(n * MAT_BYTES);
-            (boxes[i].is_r ? rm : sm) += n;
+            if (boxes[i].nlam < 1 || boxes[i].nlam > 3 || boxes[i].lam + boxes[i].nlam > 4) { printf("box directions %d\n", i); return 1; }
+            base += pad128(boxes[i].nlam * n * MAT_BYTES);
+            (boxes[i].is_r ? rm : sm) += boxes[i].nlam * n;
             const int sh = shape_index(boxes[i].e[0], boxes[i].e[1], boxes[i].e[2]);
             int e[3];
             if (sh < 0) { printf("box shape %d\n", i); return 1; }
@@ -59,8 +60,9 @@ int main(int argc, char** argv) {
                 const int ox = wrapc(x0 + b.o[0], NXg), oy = wrapc(y0 + b.o[1], NYg), oz = wrapc(z0 + b.o[2], NZg);
                 if (ox + b.e[0] > NXg || oy + b.e[1] > NYg || oz + b.e[2] > NZg) { printf("box crosses the boundary\n"); exit(1); }
                 long* dst = (is_r ? R.data() + (size_t)ring * R_BYTES / 16 : S.data() + (size_t)ring * S_BYTES / 16) + b.base / 16;
-                for (int k = 0; k < 9; k++) for (int z = 0; z < b.e[2]; z++) for (int y = 0; y < b.e[1]; y++) for (int x = 0; x < b.e[0]; x++)
-                    *dst++ = link_id(b.lam, ox + x, oy + y, oz + z, t) * 9 + k;
+                // destination = the copy's own order: [plane = (direction - lam)*9 + k][z][y][x]
+                for (int pl = 0; pl < 9 * b.nlam; pl++) for (int z = 0; z < b.e[2]; z++) for (int y = 0; y < b.e[1]; y++) for (int x = 0; x < b.e[0]; x++)
+                    *dst++ = link_id(b.lam + pl / 9, ox + x, oy + y, oz + z, t) * 9 + pl % 9;
             }
         };
         copy_part(0, tb, 0); copy_part(1, tb, 0); copy_part(0, tb + 1, 1);
