@@ -29,6 +29,9 @@
 #include "stencil.cuh"
 #include "tmarch_geom.h"
 
+#ifndef GFB_TM_UNIFORM_ISSUE
+#define GFB_TM_UNIFORM_ISSUE 0  // 1: one elected thread issues all tensor copies back to back from uniform operands (box table in constant memory); measured 32^4 0.654 ms vs 0.620, 64^4 10.33 vs 10.38: not adopted
+#endif
 #ifndef GFB_TM_DEBUG
 #define GFB_TM_DEBUG 0  // 1: no staple arithmetic (copies + operand reads only); 2: no global->shared copies (barriers only; arithmetic on stale smem)
 #endif
@@ -48,6 +51,15 @@ struct R2 {
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+// box table of tmarch_geom.h (tm::Tables::box) in constant memory: uniform loads feed the uniform-datapath TMA instructions
+__constant__ int c_tm_box[tm::NBOX][8];
+
+__device__ __forceinline__ bool elect_one() {
+    unsigned p;
+    asm volatile("{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\nselp.u32 %0, 1, 0, q;\n}\n" : "=r"(p));
+    return p != 0;
+}
+
 struct TmMaps {
     CUtensorMap m[tm::NMAP];  // per box shape and number of merged directions: tensor = [plane][z][y][2*x doubles], box = 9*nlam planes x ez x ey x 2*ex
 };
@@ -205,6 +217,7 @@ __device__ __forceinline__ void tm_run(const int MU, const TmMaps& maps, const G
 #pragma unroll
     for (int i = 0; i < tm::NDESC; i++) od[i] = tab->desc[i][tid];
 
+#if !GFB_TM_UNIFORM_ISSUE
     // ---- producer side: lane b of warp 0 owns box b (21 boxes per slice)
     const bool is_producer = tid < tm::NBOX;
     int bx_o[3] = {0, 0, 0}, b_lam = 0, b_isr = 0, b_base = 0, b_shape = 0;
@@ -212,6 +225,7 @@ __device__ __forceinline__ void tm_run(const int MU, const TmMaps& maps, const G
         bx_o[0] = tab->box[tid][0]; bx_o[1] = tab->box[tid][1]; bx_o[2] = tab->box[tid][2];
         b_lam = tab->box[tid][3]; b_isr = tab->box[tid][4]; b_base = tab->box[tid][5]; b_shape = tab->box[tid][6];
     }
+#endif
     uint64_t* const barS = bars;                 // [S_RING]
     uint64_t* const barR = bars + tm::S_RING;    // [R_RING]
     unsigned phases = 0;                         // bit s: parity of the next completion of barrier s (uniform over the CTA)
@@ -230,6 +244,26 @@ __device__ __forceinline__ void tm_run(const int MU, const TmMaps& maps, const G
         const int tb = pl.t_begin + seg * pl.seg_len;
         const int len = min(pl.seg_len, pl.t_begin + pl.t_count - tb);
 
+#if GFB_TM_UNIFORM_ISSUE
+        // one part (all its boxes) of the slice in storage slot `tslot` into ring buffer `ring`: one elected thread of warp 0
+        // issues the copies back to back; every operand is warp-uniform (tile origin, box table from constant memory), so the
+        // compiler feeds the uniform-datapath UTMALDG without the per-lane ELECT / 8 x R2UR loop of a lane-per-box issue
+        auto copy_part = [&](int is_r, int tslot, int ring) {
+            if ((tid >> 5) != 0) return;
+            uint64_t* const bar = is_r ? barR + ring : barS + ring;
+            unsigned char* const part = is_r ? sR + ring * tm::R_BYTES : sS + ring * tm::S_BYTES;
+            if (elect_one()) {
+                mbar_arrive_expect_tx(bar, (unsigned)((is_r ? tm::R_MATS : tm::S_MATS) * tm::MAT_BYTES));
+                const int b0 = is_r ? tm::NBOX_S : 0, b1 = is_r ? tm::NBOX : tm::NBOX_S;
+#pragma unroll
+                for (int b = b0; b < b1; b++) {
+                    const int bcx = 2 * wrap(x0 + c_tm_box[b][0], g.nx), bcy = wrap(y0 + c_tm_box[b][1], g.ny), bcz = wrap(z0 + c_tm_box[b][2], g.nz);
+                    tma_load_4d(smem_u32(part + c_tm_box[b][5]), &maps.m[c_tm_box[b][6]], bcx, bcy, bcz, tslot * 36 + c_tm_box[b][3] * 9, bar);
+                }
+            }
+            __syncwarp();
+        };
+#else
         const int cx = 2 * wrap(x0 + bx_o[0], g.nx), cy = wrap(y0 + bx_o[1], g.ny), cz = wrap(z0 + bx_o[2], g.nz);
         // one part (all its boxes) of the slice in storage slot `tslot` into ring buffer `ring`; warp 0 only
         auto copy_part = [&](int is_r, int tslot, int ring) {
@@ -242,6 +276,7 @@ __device__ __forceinline__ void tm_run(const int MU, const TmMaps& maps, const G
                 tma_load_4d(smem_u32(dst), &maps.m[b_shape], cx, cy, cz, tslot * 36 + b_lam * 9, bar);
             }
         };
+#endif
         auto t_up = [&](int t) { return (t == g.tloc - 1) ? g.t_up_wrap : t + 1; };
 
         // ---- prologue: slice tb (full) and the S part of slice tb+1; the backward-t staple of slice tb from global memory
@@ -423,6 +458,7 @@ const tm::Tables* device_tables(int dev) {
     tm::Tables* d = nullptr;
     if (cudaMalloc(&d, sizeof(tm::Tables)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     if (cudaMemcpy(d, &host, sizeof(tm::Tables), cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); cudaFree(d); return nullptr; }
+    if (cudaMemcpyToSymbol(c_tm_box, host.box, sizeof(host.box)) != cudaSuccess) { cudaGetLastError(); cudaFree(d); return nullptr; }
     per_dev[dev & 63] = d;
     return d;
 }

@@ -36,6 +36,7 @@ constexpr int SITES = BX * BY * BZ;      // 64 sites, 256 link-threads
 constexpr int NTHREADS = 4 * SITES;
 constexpr int MAT_BYTES = 144;
 constexpr int NBOX = 21;
+constexpr int NBOX_S = 4;               // the S part's boxes come first in the table
 constexpr int NSHAPE = 7;
 constexpr int NMAP = 3 * NSHAPE;        // tensor maps: box shape x number of merged directions (1..3)
 constexpr int S_MATS = 248, R_MATS = 428;

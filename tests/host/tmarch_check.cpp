@@ -29,6 +29,7 @@ int main(int argc, char** argv) {
             const int n = box_volume(boxes[i]);
             int& base = boxes[i].is_r ? r : s;
             if (boxes[i].base != base || (base & 127)) { printf("box base %d\n", i); return 1; }
+            if ((i < NBOX_S) != (boxes[i].is_r == 0)) { printf("S boxes must come first\n"); return 1; }
             if (boxes[i].nlam < 1 || boxes[i].nlam > 3 || boxes[i].lam + boxes[i].nlam > 4) { printf("box directions %d\n", i); return 1; }
             base += pad128(boxes[i].nlam * n * MAT_BYTES);
             (boxes[i].is_r ? rm : sm) += boxes[i].nlam * n;
