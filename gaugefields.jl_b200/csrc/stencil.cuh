@@ -128,22 +128,24 @@ __device__ __forceinline__ M3 staple_sum(const double2* __restrict__ u, const Ge
 #pragma unroll kStapleUnroll
     for (int nu = 0; nu < 4; nu++) {
         if (nu == mu) continue;
+        // two-row products (su3.cuh): the links are unitary, so rows 0,1 of A (6 of its 9 elements) carry the staple and its
+        // third row is rebuilt inside the accumulation
         {
             const Coord xn = step(g, x, nu, +1);
-            M3 a = load_link(u, g, x, nu);
-            M3 b = load_link(u, g, xn, mu);
-            M3 t = mul_nn(a, b);
-            a = load_link(u, g, xm, nu);
-            mac_nd(s, t, a);
+            const R2 a = r2_load_rows01(u + link_offset(g, x, nu), (unsigned)g.v3);
+            const M3 b = load_link(u, g, xn, mu);
+            const R2 t = r2_mul_nn(a, b);
+            const M3 c = load_link(u, g, xm, nu);
+            acc_su3(s, r2_mul_nd(t, c));
         }
         {
             const Coord xd = step(g, x, nu, -1);
             const Coord xdm = step(g, xd, mu, +1);
-            M3 a = load_link(u, g, xd, nu);
-            M3 b = load_link(u, g, xd, mu);
-            M3 t = mul_dn(a, b);
-            a = load_link(u, g, xdm, nu);
-            mac_nn(s, t, a);
+            const R2 a = r2_load_dag_rows01(u + link_offset(g, xd, nu), (unsigned)g.v3);
+            const M3 b = load_link(u, g, xd, mu);
+            const R2 t = r2_mul_nn(a, b);
+            const M3 c = load_link(u, g, xdm, nu);
+            acc_su3(s, r2_mul_nn(t, c));
         }
     }
 #endif

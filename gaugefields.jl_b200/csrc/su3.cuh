@@ -152,6 +152,104 @@ __device__ __forceinline__ void m3_add(M3& c, const M3& a) {
     for (int k = 0; k < 9; k++) { c.e[k].x += a.e[k].x; c.e[k].y += a.e[k].y; }
 }
 
+// ---- two-row arithmetic for SU(3) operands ---------------------------------------------------------------------------
+// A product of unitary links is unitary, so only its rows 0 and 1 are computed (2 x 72 FMA for a staple A B C from the first
+// two rows of A) and row 2 = conj(row0 x row1) is folded into the accumulation of the staple sum: 180 instead of 216 FP64
+// instructions per staple.  Used by both fused force kernels; every caller passes gauge links (unitary to rounding).
+struct R2 {
+    double2 e[6];  // rows 0 and 1
+};
+__device__ __forceinline__ R2 rows01(const M3& a) {
+    R2 r;
+#pragma unroll
+    for (int k = 0; k < 6; k++) r.e[k] = a.e[k];
+    return r;
+}
+__device__ __forceinline__ R2 rows01_dag(const M3& a) {
+    R2 r;
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) r.e[3 * i + j] = make_double2(a.e[3 * j + i].x, -a.e[3 * j + i].y);
+    return r;
+}
+// (2x3) * (3x3)
+__device__ __forceinline__ R2 r2_mul_nn(const R2& a, const M3& b) {
+    R2 c;
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            double2 s = cmul(a.e[3 * i], b.e[j]);
+            cmac(s, a.e[3 * i + 1], b.e[3 + j]);
+            cmac(s, a.e[3 * i + 2], b.e[6 + j]);
+            c.e[3 * i + j] = s;
+        }
+    return c;
+}
+// (2x3) * (3x3)^dagger
+__device__ __forceinline__ R2 r2_mul_nd(const R2& a, const M3& b) {
+    R2 c;
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            double2 s = make_double2(0.0, 0.0);
+            cmac_c(s, a.e[3 * i], b.e[3 * j]);
+            cmac_c(s, a.e[3 * i + 1], b.e[3 * j + 1]);
+            cmac_c(s, a.e[3 * i + 2], b.e[3 * j + 2]);
+            c.e[3 * i + j] = s;
+        }
+    return c;
+}
+// acc += conj(a*b - c*d)
+__device__ __forceinline__ void cross_acc(double2& acc, double2 a, double2 b, double2 c, double2 d) {
+    acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x); acc.x = fma(-c.x, d.x, acc.x); acc.x = fma(c.y, d.y, acc.x);
+    acc.y = fma(-a.x, b.y, acc.y); acc.y = fma(-a.y, b.x, acc.y); acc.y = fma(c.x, d.y, acc.y); acc.y = fma(c.y, d.x, acc.y);
+}
+// v += the SU(3) matrix whose rows 0,1 are r (row 2 = conj(row0 x row1))
+__device__ __forceinline__ void acc_su3(M3& v, const R2& r) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) { v.e[k].x += r.e[k].x; v.e[k].y += r.e[k].y; }
+    cross_acc(v.e[6], r.e[1], r.e[5], r.e[2], r.e[4]);
+    cross_acc(v.e[7], r.e[2], r.e[3], r.e[0], r.e[5]);
+    cross_acc(v.e[8], r.e[0], r.e[4], r.e[1], r.e[3]);
+}
+__device__ __forceinline__ M3 complete_su3(const R2& r) {
+    M3 v;
+#pragma unroll
+    for (int k = 0; k < 6; k++) v.e[k] = r.e[k];
+    v.e[6] = v.e[7] = v.e[8] = make_double2(0.0, 0.0);
+    cross_acc(v.e[6], r.e[1], r.e[5], r.e[2], r.e[4]);
+    cross_acc(v.e[7], r.e[2], r.e[3], r.e[0], r.e[5]);
+    cross_acc(v.e[8], r.e[0], r.e[4], r.e[1], r.e[3]);
+    return v;
+}
+
+// rows 0,1 of the link stored structure-of-arrays at p (element k at p + k*plane)
+__device__ __forceinline__ R2 r2_load_rows01(const double2* __restrict__ p, unsigned plane) {
+    R2 r;
+    const char* b = reinterpret_cast<const char*>(p);
+    const unsigned sb = plane * 16u;
+#pragma unroll
+    for (int k = 0; k < 6; k++) r.e[k] = __ldg(reinterpret_cast<const double2*>(b + (size_t)k * sb));
+    return r;
+}
+// rows 0,1 of its adjoint: (A^dag)[i][j] = conj(A[j][i])
+__device__ __forceinline__ R2 r2_load_dag_rows01(const double2* __restrict__ p, unsigned plane) {
+    R2 r;
+    const char* b = reinterpret_cast<const char*>(p);
+    const unsigned sb = plane * 16u;
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const double2 v = __ldg(reinterpret_cast<const double2*>(b + (size_t)(3 * j + i) * sb));
+            r.e[3 * i + j] = make_double2(v.x, -v.y);
+        }
+    return r;
+}
+
 // structure-of-arrays access: element k of the matrix lives `k*plane` elements after element 0.
 // The address of element k is formed as base + k*(plane*16) with a 32-bit byte stride, which ptxas
 // turns into ONE IMAD.WIDE.U32 per 128-bit access (64-bit index arithmetic costs 4 integer

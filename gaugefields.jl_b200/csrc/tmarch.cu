@@ -46,9 +46,6 @@ struct TmPlan {
     int ntx, nty, ntz, ntiles;
 };
 
-struct R2 {
-    double2 e[6];  // rows 0 and 1
-};
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 // box table of tmarch_geom.h (tm::Tables::box) in constant memory: uniform loads feed the uniform-datapath TMA instructions
@@ -130,73 +127,6 @@ __device__ __forceinline__ R2 lds_dag_rows01(const SmOp& o) {
         }
     return r;
 }
-__device__ __forceinline__ R2 rows01(const M3& a) {
-    R2 r;
-#pragma unroll
-    for (int k = 0; k < 6; k++) r.e[k] = a.e[k];
-    return r;
-}
-__device__ __forceinline__ R2 rows01_dag(const M3& a) {
-    R2 r;
-#pragma unroll
-    for (int i = 0; i < 2; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) r.e[3 * i + j] = make_double2(a.e[3 * j + i].x, -a.e[3 * j + i].y);
-    return r;
-}
-// (2x3) * (3x3)
-__device__ __forceinline__ R2 r2_mul_nn(const R2& a, const M3& b) {
-    R2 c;
-#pragma unroll
-    for (int i = 0; i < 2; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            double2 s = cmul(a.e[3 * i], b.e[j]);
-            cmac(s, a.e[3 * i + 1], b.e[3 + j]);
-            cmac(s, a.e[3 * i + 2], b.e[6 + j]);
-            c.e[3 * i + j] = s;
-        }
-    return c;
-}
-// (2x3) * (3x3)^dagger
-__device__ __forceinline__ R2 r2_mul_nd(const R2& a, const M3& b) {
-    R2 c;
-#pragma unroll
-    for (int i = 0; i < 2; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            double2 s = make_double2(0.0, 0.0);
-            cmac_c(s, a.e[3 * i], b.e[3 * j]);
-            cmac_c(s, a.e[3 * i + 1], b.e[3 * j + 1]);
-            cmac_c(s, a.e[3 * i + 2], b.e[3 * j + 2]);
-            c.e[3 * i + j] = s;
-        }
-    return c;
-}
-// acc += conj(a*b - c*d)
-__device__ __forceinline__ void cross_acc(double2& acc, double2 a, double2 b, double2 c, double2 d) {
-    acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x); acc.x = fma(-c.x, d.x, acc.x); acc.x = fma(c.y, d.y, acc.x);
-    acc.y = fma(-a.x, b.y, acc.y); acc.y = fma(-a.y, b.x, acc.y); acc.y = fma(c.x, d.y, acc.y); acc.y = fma(c.y, d.x, acc.y);
-}
-// v += the SU(3) matrix whose rows 0,1 are r (row 2 = conj(row0 x row1))
-__device__ __forceinline__ void acc_su3(M3& v, const R2& r) {
-#pragma unroll
-    for (int k = 0; k < 6; k++) { v.e[k].x += r.e[k].x; v.e[k].y += r.e[k].y; }
-    cross_acc(v.e[6], r.e[1], r.e[5], r.e[2], r.e[4]);
-    cross_acc(v.e[7], r.e[2], r.e[3], r.e[0], r.e[5]);
-    cross_acc(v.e[8], r.e[0], r.e[4], r.e[1], r.e[3]);
-}
-__device__ __forceinline__ M3 complete_su3(const R2& r) {
-    M3 v;
-#pragma unroll
-    for (int k = 0; k < 6; k++) v.e[k] = r.e[k];
-    v.e[6] = v.e[7] = v.e[8] = make_double2(0.0, 0.0);
-    cross_acc(v.e[6], r.e[1], r.e[5], r.e[2], r.e[4]);
-    cross_acc(v.e[7], r.e[2], r.e[3], r.e[0], r.e[5]);
-    cross_acc(v.e[8], r.e[0], r.e[4], r.e[1], r.e[3]);
-    return v;
-}
-
 __device__ __forceinline__ int wrap(int c, int n) { return c < 0 ? c + n : (c >= n ? c - n : c); }
 
 // The whole persistent loop of one link-thread.  mu is warp-uniform but NOT a template parameter: all eight warps run the same
