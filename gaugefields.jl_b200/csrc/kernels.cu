@@ -77,8 +77,7 @@ k_force_fused(Geom g, int t_begin, int t_count, const double2* __restrict__ uin,
         if (WRITE_Z) *reinterpret_cast<double*>(reinterpret_cast<char*>(zout + zo) + (size_t)k * zsb) = v;
     }
     if (DO_EXP) {
-        M3 e = exp_ta(z, c);
-        M3 r = mul_nn(e, umu);
+        const M3 r = exp_ta_times_su3(z, c, umu);
         store_link(uout, g, x, mu, r);
     }
 }

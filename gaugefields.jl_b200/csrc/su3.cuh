@@ -481,6 +481,13 @@ __device__ __forceinline__ M3 exp_iH(const H3& qin) {
 // exp(t * sum_a c_a i lambda_a/2)
 __device__ __forceinline__ M3 exp_ta(const double* c, double t) { return exp_iH(h3_from_coeffs(c, t)); }
 
+// exp(t * sum_a c_a i lambda_a/2) * U for a unitary U: the product is unitary, so rows 0,1 are computed (the third row of the
+// exponential is then dead code) and row 2 = conj(row0 x row1): 96 instead of 108 FP64 instructions, ~24 less in the exponential
+__device__ __forceinline__ M3 exp_ta_times_su3(const double* c, double t, const M3& u) {
+    const M3 e = exp_ta(c, t);
+    return complete_su3(r2_mul_nn(rows01(e), u));
+}
+
 // SU(3) reunitarisation (src/4D/nowing/gaugefields_4D_nowing.jl:2387-2458, :195-238)
 __device__ __forceinline__ M3 reunitarize(const M3& m) {
     M3 u = m;

@@ -317,8 +317,7 @@ __device__ __forceinline__ void tm_run(const int MU, const TmMaps& maps, const G
                 if (WRITE_Z) *reinterpret_cast<double*>(reinterpret_cast<char*>(zout + zo) + (size_t)k * zsb) = v;
             }
             if (DO_EXP) {
-                const M3 e = exp_ta(f, c);
-                const M3 r = mul_nn(e, U);
+                const M3 r = exp_ta_times_su3(f, c, U);
                 const unsigned uo = (unsigned)(t * 36 + MU * 9) * (unsigned)g.v3 + s3;
                 m3_store(uout + uo, (unsigned)g.v3, r);
             }
