@@ -500,6 +500,46 @@ int gfb_gauge_download(const gfb_gauge* g, int mu, double* host) {
     for (auto& s : ctx->slabs) { GFB_CUDA(ctx, cudaSetDevice(s.device)); GFB_CUDA(ctx, cudaStreamSynchronize(s.stream)); }
     return GFB_OK;
 }
+int gfb_gauge_upload_ildg(gfb_gauge* g, const void* payload, int precision) {
+    if (!g || !payload) return fail(g ? g->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = g->ctx;
+    if (precision != 32 && precision != 64) return fail(ctx, GFB_ERR_ARG, "ILDG precision must be 32 or 64");
+    const size_t v3 = (size_t)g->nx * g->ny * g->nz;
+    const size_t site_bytes = (size_t)4 * 9 * 2 * (precision / 8);
+    const size_t bytes = v3 * g->tloc * site_bytes;
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        Slab& s = ctx->slabs[i];
+        GFB_CHECK(ensure_staging(ctx, s, bytes));
+        GFB_CUDA(ctx, cudaSetDevice(s.device));
+        Geom geo = geom_of(g, i);
+        const char* src = reinterpret_cast<const char*>(payload) + (size_t)geo.t0 * v3 * site_bytes;
+        GFB_CUDA(ctx, cudaMemcpyAsync(s.d_staging, src, bytes, cudaMemcpyHostToDevice, s.stream));
+        launch_links_from_ildg(s.stream, geo, precision, s.d_staging, g->d[i]);
+        GFB_CHECK(post_launch(ctx));
+    }
+    g->halo_valid = false;
+    return GFB_OK;
+}
+int gfb_gauge_download_ildg(const gfb_gauge* g, void* payload, int precision) {
+    if (!g || !payload) return fail(g ? g->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = g->ctx;
+    if (precision != 32 && precision != 64) return fail(ctx, GFB_ERR_ARG, "ILDG precision must be 32 or 64");
+    const size_t v3 = (size_t)g->nx * g->ny * g->nz;
+    const size_t site_bytes = (size_t)4 * 9 * 2 * (precision / 8);
+    const size_t bytes = v3 * g->tloc * site_bytes;
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        Slab& s = ctx->slabs[i];
+        GFB_CHECK(ensure_staging(ctx, s, bytes));
+        GFB_CUDA(ctx, cudaSetDevice(s.device));
+        Geom geo = geom_of(g, i);
+        launch_links_to_ildg(s.stream, geo, precision, g->d[i], s.d_staging);
+        GFB_CHECK(post_launch(ctx));
+        char* dst = reinterpret_cast<char*>(payload) + (size_t)geo.t0 * v3 * site_bytes;
+        GFB_CUDA(ctx, cudaMemcpyAsync(dst, s.d_staging, bytes, cudaMemcpyDeviceToHost, s.stream));
+    }
+    for (auto& s : ctx->slabs) { GFB_CUDA(ctx, cudaSetDevice(s.device)); GFB_CUDA(ctx, cudaStreamSynchronize(s.stream)); }
+    return GFB_OK;
+}
 int gfb_mom_upload(gfb_mom* p, int mu, const double* host) {
     if (!p || !host) return fail(p ? p->ctx : nullptr, GFB_ERR_ARG, "null argument");
     gfb_ctx* ctx = p->ctx;

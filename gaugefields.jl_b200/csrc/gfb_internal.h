@@ -127,6 +127,9 @@ int plaquette_blocks(const Geom& g);
 int sumsq_blocks(size_t n);
 void launch_links_from_host_layout(cudaStream_t st, const Geom& g, int mu, const double2* staging, double2* u);
 void launch_links_to_host_layout(cudaStream_t st, const Geom& g, int mu, const double2* u, double2* staging);
+// ILDG payload (big-endian [t][z][y][x][mu][row][col], 32- or 64-bit) <-> device layout for this slab's time-slices
+void launch_links_from_ildg(cudaStream_t st, const Geom& g, int precision, const void* payload, double2* u);
+void launch_links_to_ildg(cudaStream_t st, const Geom& g, int precision, const double2* u, void* payload);
 void launch_mom_from_host_layout(cudaStream_t st, const Geom& g, int mu, const double* staging, double* p);
 void launch_mom_to_host_layout(cudaStream_t st, const Geom& g, int mu, const double* p, double* staging);
 void launch_set_cold(cudaStream_t st, const Geom& g, double2* u);

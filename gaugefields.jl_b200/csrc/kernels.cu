@@ -351,6 +351,77 @@ __global__ void __launch_bounds__(256) k_links_to_host(Geom g, int mu, const dou
 #pragma unroll
         for (int j = 0; j < 3; j++) dst[i + 3 * j] = src[(size_t)(3 * i + j) * g.v3];
 }
+// ILDG binary payload (big-endian, [t][z][y][x][mu][row][col] complex; src/output/ildg_format.jl:697-746 writes it site by
+// site on the host) <-> device layout: byte swap, precision conversion and the AoS -> SoA transpose in one pass over the slab,
+// so a production configuration goes file -> pinned buffer -> GPU without a host-side reshuffle.  One thread per local site.
+__device__ __forceinline__ unsigned long long bswap64(unsigned long long v) {
+    const unsigned lo = (unsigned)v, hi = (unsigned)(v >> 32);
+    return ((unsigned long long)__byte_perm(lo, 0, 0x0123) << 32) | __byte_perm(hi, 0, 0x0123);
+}
+template <typename F>
+__global__ void __launch_bounds__(256) k_links_from_ildg(Geom g, const void* __restrict__ payload, double2* __restrict__ u) {
+    const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= (long)g.v3 * g.tloc) return;
+    const int t = (int)(n / g.v3);
+    const int s3 = (int)(n - (long)t * g.v3);
+#pragma unroll 1
+    for (int mu = 0; mu < 4; mu++) {
+        double2* dst = u + (size_t)(t * 36 + mu * 9) * g.v3 + s3;
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            const size_t e = ((size_t)n * 4 + mu) * 9 + k;  // complex element index in the payload
+            double re, im;
+            if (sizeof(F) == 8) {
+                const unsigned long long* src = reinterpret_cast<const unsigned long long*>(payload) + 2 * e;
+                re = __longlong_as_double((long long)bswap64(src[0]));
+                im = __longlong_as_double((long long)bswap64(src[1]));
+            } else {
+                const unsigned* src = reinterpret_cast<const unsigned*>(payload) + 2 * e;
+                re = (double)__uint_as_float(__byte_perm(src[0], 0, 0x0123));
+                im = (double)__uint_as_float(__byte_perm(src[1], 0, 0x0123));
+            }
+            dst[(size_t)k * g.v3] = make_double2(re, im);
+        }
+    }
+}
+template <typename F>
+__global__ void __launch_bounds__(256) k_links_to_ildg(Geom g, const double2* __restrict__ u, void* __restrict__ payload) {
+    const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= (long)g.v3 * g.tloc) return;
+    const int t = (int)(n / g.v3);
+    const int s3 = (int)(n - (long)t * g.v3);
+#pragma unroll 1
+    for (int mu = 0; mu < 4; mu++) {
+        const double2* src = u + (size_t)(t * 36 + mu * 9) * g.v3 + s3;
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            const size_t e = ((size_t)n * 4 + mu) * 9 + k;
+            const double2 v = src[(size_t)k * g.v3];
+            if (sizeof(F) == 8) {
+                unsigned long long* dst = reinterpret_cast<unsigned long long*>(payload) + 2 * e;
+                dst[0] = bswap64((unsigned long long)__double_as_longlong(v.x));
+                dst[1] = bswap64((unsigned long long)__double_as_longlong(v.y));
+            } else {
+                unsigned* dst = reinterpret_cast<unsigned*>(payload) + 2 * e;
+                dst[0] = __byte_perm(__float_as_uint((float)v.x), 0, 0x0123);
+                dst[1] = __byte_perm(__float_as_uint((float)v.y), 0, 0x0123);
+            }
+        }
+    }
+}
+void launch_links_from_ildg(cudaStream_t st, const Geom& g, int precision, const void* payload, double2* u) {
+    const long n = (long)g.v3 * g.tloc;
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    if (precision == 64) k_links_from_ildg<double><<<nb, 256, 0, st>>>(g, payload, u);
+    else k_links_from_ildg<float><<<nb, 256, 0, st>>>(g, payload, u);
+}
+void launch_links_to_ildg(cudaStream_t st, const Geom& g, int precision, const double2* u, void* payload) {
+    const long n = (long)g.v3 * g.tloc;
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    if (precision == 64) k_links_to_ildg<double><<<nb, 256, 0, st>>>(g, u, payload);
+    else k_links_to_ildg<float><<<nb, 256, 0, st>>>(g, u, payload);
+}
+
 __global__ void __launch_bounds__(256) k_mom_from_host(Geom g, int mu, const double* __restrict__ staging, double* __restrict__ p) {
     const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= (long)g.v3 * g.tloc) return;

@@ -35,6 +35,8 @@ SIGNATURES = {
     "gfb_mom_free": (c_int, [c_void_p]),
     "gfb_gauge_upload": (c_int, [c_void_p, c_int, c_void_p]),
     "gfb_gauge_download": (c_int, [c_void_p, c_int, c_void_p]),
+    "gfb_gauge_upload_ildg": (c_int, [c_void_p, c_void_p, c_int]),
+    "gfb_gauge_download_ildg": (c_int, [c_void_p, c_void_p, c_int]),
     "gfb_mom_upload": (c_int, [c_void_p, c_int, c_void_p]),
     "gfb_mom_download": (c_int, [c_void_p, c_int, c_void_p]),
     "gfb_gauge_copy": (c_int, [c_void_p, c_void_p]),
@@ -88,6 +90,23 @@ class GfbError(RuntimeError):
     """A non-zero status from libgfb200 (the Julia glue throws ErrorException here)."""
 
 
+def _preload_bundled_nccl():
+    """libgfb200.so needs `libnccl.so.2`; so does PyTorch, which ships a NEWER one (site-packages/nvidia/nccl/lib) than the
+    system library the dynamic loader would pick for us.  Whichever copy is mapped first serves both, and `import torch`
+    fails on the older one (undefined symbol), so map the bundled copy first when it exists.  Harmless if torch is absent."""
+    try:
+        import importlib.util
+
+        spec = importlib.util.find_spec("nvidia")
+        for base in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(base, "nccl", "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                ctypes.CDLL(cand, mode=ctypes.RTLD_GLOBAL)
+                return
+    except Exception:  # noqa: BLE001 -- fall back to the loader's choice
+        pass
+
+
 def load():
     global _lib
     if _lib is not None:
@@ -97,6 +116,7 @@ def load():
             "libgfb200.so is not built (%s). Run `python gaugefields.jl_b200/build.py`; "
             "there is no CPU fallback." % LIB_PATH
         )
+    _preload_bundled_nccl()
     lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol

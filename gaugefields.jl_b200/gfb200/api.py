@@ -242,6 +242,32 @@ class GaugeConfiguration:
         return out
 
 
+    def upload_ildg(self, payload, precision=64):
+        """Load the ILDG binary payload of the whole lattice (big-endian [t][z][y][x][mu][row][col], src/output/ildg_format.jl:67-83);
+        byte swap, precision conversion and transpose run on the GPU.  `payload`: bytes-like of the global lattice."""
+        nx, ny, nz, nt = self.lattice
+        buf = np.frombuffer(payload, dtype=np.uint8)
+        want = nx * ny * nz * nt * 4 * 9 * 2 * (precision // 8)
+        if precision not in (32, 64):
+            raise ValueError("ILDG precision must be 32 or 64")
+        if buf.size != want:
+            raise ValueError("ILDG payload has %d bytes; expected %d" % (buf.size, want))
+        buf = np.ascontiguousarray(buf)
+        self.backend.call("gfb_gauge_upload_ildg", self._h, ctypes.c_void_p(buf.ctypes.data), precision)
+        self.backend.sync()
+        return self
+
+    def to_ildg(self, precision=64):
+        """ILDG binary payload (bytes) of the whole lattice (_save_binarydata, src/output/ildg_format.jl:697-746).
+        One-process-per-GPU: only this rank's time-slices are filled."""
+        nx, ny, nz, nt = self.lattice
+        if precision not in (32, 64):
+            raise ValueError("ILDG precision must be 32 or 64")
+        out = np.zeros(nx * ny * nz * nt * 4 * 9 * 2 * (precision // 8), dtype=np.uint8)
+        self.backend.call("gfb_gauge_download_ildg", self._h, ctypes.c_void_p(out.ctypes.data), precision)
+        return out.tobytes()
+
+
 class Momenta:
     """Conjugate momenta: four 8-coefficient fields (initialize_TA_Gaugefields, src/TA_Gaugefields.jl:140-195)."""
 

@@ -80,6 +80,12 @@ int gfb_mom_free(gfb_mom* p);
 /* host <-> device in the gathered layout (gather_matrix, src/API.jl:516-533); host = global array of one direction */
 int gfb_gauge_upload(gfb_gauge* g, int mu, const double* host);
 int gfb_gauge_download(const gfb_gauge* g, int mu, double* host);
+/* ILDG binary payload of the whole lattice (big-endian, [t][z][y][x][mu][row][col] complex, 32- or 64-bit floats: what
+ * _save_binarydata writes and load_gaugefield! reads site by site, src/output/ildg_format.jl:697-746, 67-83) <-> device.
+ * Byte swap, precision conversion and the layout transpose run on the GPU; in one-process-per-GPU mode every rank passes the
+ * global payload pointer and reads/writes only its own time-slices.  The LIME container is the host's business. */
+int gfb_gauge_upload_ildg(gfb_gauge* g, const void* payload, int precision);
+int gfb_gauge_download_ildg(const gfb_gauge* g, void* payload, int precision);
 int gfb_mom_upload(gfb_mom* p, int mu, const double* host);
 int gfb_mom_download(const gfb_mom* p, int mu, double* host);
 /* copy_configuration! / substitute_U! (src/API.jl:307-322) */

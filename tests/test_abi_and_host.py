@@ -18,7 +18,9 @@ def header_symbols():
 
 def test_library_exports_every_declared_symbol():
     import gfb200
+    from gfb200 import _lib
 
+    _lib._preload_bundled_nccl()  # same NCCL copy as a later `import torch` in this process (see _lib.load)
     lib = ctypes.CDLL(gfb200.LIB_PATH)
     syms = header_symbols()
     assert len(syms) >= 40
