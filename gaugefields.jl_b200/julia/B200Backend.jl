@@ -152,6 +152,23 @@ function scatter_global_array!(u::Gaugefields_4D_B200, A::Array{ComplexF64,6})
     _gfb_check(ccall((:gfb_gauge_upload, LIBGFB200), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), u.handle.ptr, u.mu - 1, A), u.handle.ctx.ptr)
     return u
 end
+# ILDG binary payload (the ildg-binary-data record as it is in the file: big-endian [t][z][y][x][mu][row][col], precision 32
+# or 64) <-> device; replaces the site-by-site host loops of load_gaugefield! / _save_binarydata
+# (src/output/ildg_format.jl:67-83, 697-746).  Byte swap, precision conversion and transpose run on the GPU.
+function scatter_ildg_payload!(U::AbstractVector{<:Gaugefields_4D_B200}, payload::Vector{UInt8}, precision::Integer)
+    u = first(U)
+    length(payload) == u.NX * u.NY * u.NZ * u.NT * 4 * 9 * 2 * (precision ÷ 8) ||
+        throw(DimensionMismatch("ILDG payload has $(length(payload)) bytes"))
+    _gfb_check(ccall((:gfb_gauge_upload_ildg, LIBGFB200), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint), u.handle.ptr, payload, precision), u.handle.ctx.ptr)
+    return U
+end
+function gather_ildg_payload(U::AbstractVector{<:Gaugefields_4D_B200}, precision::Integer)
+    u = first(U)
+    payload = Vector{UInt8}(undef, u.NX * u.NY * u.NZ * u.NT * 4 * 9 * 2 * (precision ÷ 8))
+    _gfb_check(ccall((:gfb_gauge_download_ildg, LIBGFB200), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint), u.handle.ptr, payload, precision), u.handle.ctx.ptr)
+    return payload
+end
+
 # slow-path element access (generic code and tests index fields directly)
 Base.getindex(u::Gaugefields_4D_B200, i, j, x, y, z, t) = gather_global_array(u)[i, j, x, y, z, t]
 
