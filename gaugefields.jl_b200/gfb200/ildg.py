@@ -86,3 +86,29 @@ def write_ildg(filename, lattice, precision, payload):
     with open(filename, "wb") as f:
         f.write(_record("ildg-format", format_xml(lattice, precision).encode("utf-8"), True, False))
         f.write(_record("ildg-binary-data", bytes(payload), False, True))
+
+
+# ---- Bridge++ text format (src/output/bridge_format.jl:201-297: save_textdata / load_BridgeText!) --------------------------
+# One decimal number per line, real then imaginary part, in the SAME element order as the ILDG payload
+# ([t][z][y][x][mu][a][b]); so a text file is converted to/from the 64-bit ILDG payload and takes the same device path.
+def read_bridge_text(filename, lattice, nc=3):
+    """64-bit ILDG payload (bytes) of a Bridge++ text configuration; raises ValueError when the line count is wrong
+    (the reference asserts 4*NX*NY*NZ*NT*NC*NC*2 lines)."""
+    import numpy as np
+
+    want = 4 * lattice[0] * lattice[1] * lattice[2] * lattice[3] * nc * nc * 2
+    with open(filename) as f:
+        vals = np.array([float(line.split()[0]) for line in f if line.strip()], dtype=np.float64)
+    if vals.size != want:
+        raise ValueError("Bridge text file has %d numbers; expected %d" % (vals.size, want))
+    return vals.astype(">f8").tobytes()
+
+
+def write_bridge_text(filename, payload):
+    """Inverse of read_bridge_text for a 64-bit payload (repr round-trips a double exactly)."""
+    import numpy as np
+
+    vals = np.frombuffer(payload, dtype=">f8")
+    with open(filename, "w") as f:
+        f.write("\n".join(repr(float(v)) for v in vals))
+        f.write("\n")

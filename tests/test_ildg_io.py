@@ -33,6 +33,26 @@ def test_lime_container_round_trip(tmp_path):
     assert os.path.getsize(fn) % 8 == 0
 
 
+def test_bridge_text_is_the_ildg_order_in_decimal(tmp_path):
+    """save_textdata / load_BridgeText! (src/output/bridge_format.jl:201-297) use the ILDG element order, one number per line."""
+    from gfb200 import ildg
+
+    lattice = (2, 2, 2, 2)
+    rng = np.random.default_rng(3)
+    Uh = rng.normal(size=(4, 2, 2, 2, 2, 3, 3)) + 1j * rng.normal(size=(4, 2, 2, 2, 2, 3, 3))
+    payload = payload_of(Uh, 64)
+    fn = str(tmp_path / "conf.txt")
+    ildg.write_bridge_text(fn, payload)
+    lines = open(fn).read().split()
+    assert len(lines) == 4 * 16 * 9 * 2
+    # first link of the file: site (1,1,1,1), mu = 1, element (a=1,b=1) real, imaginary; then (a=1,b=2)
+    assert float(lines[0]) == Uh[0, 0, 0, 0, 0, 0, 0].real and float(lines[1]) == Uh[0, 0, 0, 0, 0, 0, 0].imag
+    assert float(lines[2]) == Uh[0, 0, 0, 0, 0, 1, 0].real  # U[a=1,b=2]: row 1, col 2 -> gathered array index [col, row]
+    assert ildg.read_bridge_text(fn, lattice) == payload
+    with pytest.raises(ValueError):
+        ildg.read_bridge_text(fn, (2, 2, 2, 4))
+
+
 @pytest.mark.parametrize("name", ["conf_00000100_4444nc2.ildg", "conf_00000100_4444_test.ildg"])
 def test_reads_the_reference_fixture_files(name):
     """The reference ships two 4^4 ILDG files (test/data); they are SU(2), so only the container and the size logic apply."""
