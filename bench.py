@@ -271,6 +271,8 @@ def main():
         kern_ms = ms / K
     else:
         tiled = nx % 8 == 0 and ny % 4 == 0 and nz % 2 == 0 and os.environ.get("GFB200_TMARCH", "1") != "0"
+        if world > 1 and tl - 2 < 8 and os.environ.get("GFB200_TMARCH", "1") != "2":
+            tiled = False  # short slab interiors stay in k_force_fused (csrc/tmarch.cu, launch_tmarch_fused)
         kern = ("k_tmarch_fused<READ_Z,WRITE_Z,DO_EXP>" if tiled else "k_force_fused<READ_Z,WRITE_Z,DO_EXP>") + " (staple->TA force->momentum kick->exp(eps P) U)"
         kern_bytes = 2 * U_BYTES + 2 * P_BYTES
         kern_ms = max(ms - t_extra, 1e-9) / K

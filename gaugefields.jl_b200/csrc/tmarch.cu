@@ -446,6 +446,10 @@ bool launch_tmarch_fused(cudaStream_t st, const Geom& g, int t_begin, int t_coun
     const int mode = em ? atoi(em) : 1;
     if (!mode) return false;
     if (g.t_stride != 1 || t_count < 2) return false;
+    // Short slab interiors stay in k_force_fused: with 8 slices per GPU (6 interior) the step is set by the exchange chain, a
+    // segment start is 10 % of a 6-slice march, and all-k_force_fused measured 3-6 % faster on 8 GPUs (profiles/r1_tmarch.md);
+    // from 16 slices per GPU on the t-marching interior wins (2.98 vs ~3.6 ms at 64^4 on 4 GPUs).  GFB200_TMARCH=2 forces it.
+    if (g.nslots > g.tloc && t_count < 8 && mode != 2) return false;
     if (g.nx % tm::BX || g.ny % tm::BY || g.nz % tm::BZ) return false;
     if (uout == uin) return false;
     int dev = 0;

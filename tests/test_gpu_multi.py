@@ -36,9 +36,11 @@ DIMS = (4, 6, 4, 8)
 # (8, 4, 2, 12): the 8x4x2 tile divides the lattice, so whole-slab passes and the interior slices of the split passes run in
 # the t-marching kernel (halo slots read through TMA and through the segment prologue), the two boundary slices in k_force_fused
 @pytest.mark.parametrize("dims", [DIMS, (8, 4, 2, 12)])
-def test_two_slabs_match_oracle(backend2, oracle, dims):
+def test_two_slabs_match_oracle(backend2, oracle, dims, monkeypatch):
     import gfb200
 
+    # slabs this thin would stay in k_force_fused (the library keeps interiors under 8 slices there): force the tile kernel
+    monkeypatch.setenv("GFB200_TMARCH", "2")
     Uh = oracle.hot_start_philox(dims, 1234)
     U = gfb200.gauge_configuration(dims, backend=backend2).upload(Uh)
     assert gfb200.gauge_process_grid(U) == (1, 1, 1, 2)
