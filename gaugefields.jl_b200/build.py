@@ -10,8 +10,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["kernels.cu", "tmarch.cu", "rowtile.cu", "stout.cu", "primitives.cu", "api.cu"]
-HEADERS = ["su3.cuh", "lattice.cuh", "stencil.cuh", "rowtile_tables.h", "tmarch_geom.h", "gfb_internal.h", os.path.join("..", "..", "include", "gfb200.h")]
+SOURCES = ["kernels.cu", "tmarch.cu", "stout.cu", "primitives.cu", "api.cu"]
+HEADERS = ["su3.cuh", "lattice.cuh", "stencil.cuh", "tmarch_geom.h", "gfb_internal.h", os.path.join("..", "..", "include", "gfb200.h")]
 # GFB200_VARIANT=<name> + GFB200_NVCC_EXTRA="-D..." build a tuning variant next to the default library
 VARIANT = os.environ.get("GFB200_VARIANT", "")
 LIB = os.path.join(HERE, "libgfb200%s.so" % (("_" + VARIANT) if VARIANT else ""))

@@ -96,13 +96,90 @@ static int init_slab(gfb_ctx* ctx, Slab& s) {
     GFB_CUDA(ctx, cudaEventCreate(&s.ev_toc));
     GFB_CUDA(ctx, cudaMalloc(&s.d_result, 64 * sizeof(double)));
     GFB_CUDA(ctx, cudaMallocHost(&s.h_result, 64 * sizeof(double)));
+    GFB_CUDA(ctx, cudaMalloc(&s.d_flags, 64));
+    GFB_CUDA(ctx, cudaMemset(s.d_flags, 0, 64));
     return GFB_OK;
 }
 
+// ---- peer access for the halo exchange by peer stores -------------------------------------------------------------------
+// One process, several GPUs: enable peer access between ring neighbours; the neighbours' buffers are ordinary pointers.
+static bool setup_peers_local(gfb_ctx* ctx) {
+    const int n = (int)ctx->slabs.size();
+    if (n < 2) return false;
+    for (int i = 0; i < n; i++) {
+        const int nb[2] = {(i + n - 1) % n, (i + 1) % n};
+        for (int k = 0; k < 2; k++) {
+            const int a = ctx->slabs[i].device, b = ctx->slabs[nb[k]].device;
+            if (a == b) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, a, b) != cudaSuccess || !can) { cudaGetLastError(); return false; }
+            cudaSetDevice(a);
+            cudaError_t e = cudaDeviceEnablePeerAccess(b, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return false; }
+            cudaGetLastError();
+        }
+        ctx->slabs[i].peer_flag_prev = ctx->slabs[nb[0]].d_flags + 1;
+        ctx->slabs[i].peer_flag_next = ctx->slabs[nb[1]].d_flags + 0;
+    }
+    return true;
+}
+// One process per GPU: all-gather the CUDA IPC handle of `mine` over NCCL and map the two ring neighbours' allocations.
+// Collective: every rank calls it at the same point (buffer allocation is collective in the SPMD host programs).
+static int exchange_ipc(gfb_ctx* ctx, void* mine, void** prev, void** next) {
+    Slab& s = ctx->slabs[0];
+    const int G = ctx->nslabs_total, r = s.index;
+    GFB_CUDA(ctx, cudaSetDevice(s.device));
+    cudaIpcMemHandle_t h;
+    GFB_CUDA(ctx, cudaIpcGetMemHandle(&h, mine));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    GFB_CHECK(ensure_staging(ctx, s, (size_t)64 * (G + 1)));
+    char* stg = reinterpret_cast<char*>(s.d_staging);
+    GFB_CUDA(ctx, cudaMemcpyAsync(stg, &h, 64, cudaMemcpyHostToDevice, s.stream));
+    GFB_NCCL(ctx, ncclAllGather(stg, stg + 64, 64, ncclChar, s.nccl, s.stream));
+    std::vector<char> all((size_t)64 * G);
+    GFB_CUDA(ctx, cudaMemcpyAsync(all.data(), stg + 64, (size_t)64 * G, cudaMemcpyDeviceToHost, s.stream));
+    GFB_CUDA(ctx, cudaStreamSynchronize(s.stream));
+    auto open = [&](int rank, void** out) -> int {
+        const std::string key(all.data() + (size_t)64 * rank, 64);
+        auto it = ctx->ipc_opened.find(key);
+        if (it != ctx->ipc_opened.end()) { *out = it->second; return GFB_OK; }
+        cudaIpcMemHandle_t hh;
+        std::memcpy(&hh, key.data(), 64);
+        void* ptr = nullptr;
+        GFB_CUDA(ctx, cudaIpcOpenMemHandle(&ptr, hh, cudaIpcMemLazyEnablePeerAccess));
+        ctx->ipc_opened[key] = ptr;
+        *out = ptr;
+        return GFB_OK;
+    };
+    GFB_CHECK(open((r + G - 1) % G, prev));
+    GFB_CHECK(open((r + 1) % G, next));
+    return GFB_OK;
+}
+static bool setup_peers_distributed(gfb_ctx* ctx) {
+    Slab& s = ctx->slabs[0];
+    void *pp = nullptr, *pn = nullptr;
+    int st = exchange_ipc(ctx, s.d_flags, &pp, &pn);
+    // every rank must take the same path: agree on the outcome (sum of failures) before trusting it
+    int bad = (st != GFB_OK) ? 1 : 0;
+    if (cudaMemcpy(s.d_result, &bad, sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) return false;
+    if (ncclAllReduce(s.d_result, s.d_result, 1, ncclInt, ncclSum, s.nccl, s.stream) != ncclSuccess) return false;
+    if (cudaMemcpyAsync(&bad, s.d_result, sizeof(int), cudaMemcpyDeviceToHost, s.stream) != cudaSuccess) return false;
+    if (cudaStreamSynchronize(s.stream) != cudaSuccess) return false;
+    if (bad) { cudaGetLastError(); return false; }
+    s.peer_flag_prev = reinterpret_cast<unsigned*>(pp) + 1;
+    s.peer_flag_next = reinterpret_cast<unsigned*>(pn) + 0;
+    return true;
+}
+static bool peer_halo_wanted() {
+    const char* e = getenv("GFB200_HALO");  // "nccl": keep the send/recv exchange; default "peer"
+    return !(e && std::string(e) == "nccl");
+}
+
 // Sum one scalar per local slab (already in d_result[slot]) over all slabs of all ranks, in slab order.
-static int gather_scalars(gfb_ctx* ctx, int nslots, double* out) {
+static int gather_scalars(gfb_ctx* ctx, int nslots, double* out, bool take_max = false) {
     const int G = ctx->nslabs_total;
     for (int k = 0; k < nslots; k++) out[k] = 0.0;
+    auto fold = [&](double& acc, double v) { acc = take_max ? (v > acc || v != v ? v : acc) : acc + v; };
     if (!ctx->distributed) {
         for (auto& s : ctx->slabs) {
             GFB_CUDA(ctx, cudaSetDevice(s.device));
@@ -111,7 +188,7 @@ static int gather_scalars(gfb_ctx* ctx, int nslots, double* out) {
         for (auto& s : ctx->slabs) {
             GFB_CUDA(ctx, cudaSetDevice(s.device));
             GFB_CUDA(ctx, cudaStreamSynchronize(s.stream));
-            for (int k = 0; k < nslots; k++) out[k] += s.h_result[k];
+            for (int k = 0; k < nslots; k++) fold(out[k], s.h_result[k]);
         }
         return GFB_OK;
     }
@@ -123,7 +200,7 @@ static int gather_scalars(gfb_ctx* ctx, int nslots, double* out) {
     GFB_CUDA(ctx, cudaMemcpyAsync(s.h_result, s.d_result + 8, (size_t)nslots * G * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
     GFB_CUDA(ctx, cudaStreamSynchronize(s.stream));
     for (int r = 0; r < G; r++)
-        for (int k = 0; k < nslots; k++) out[k] += s.h_result[r * nslots + k];
+        for (int k = 0; k < nslots; k++) fold(out[k], s.h_result[r * nslots + k]);
     return GFB_OK;
 }
 
@@ -139,6 +216,13 @@ static int gather_scalars(gfb_ctx* ctx, int nslots, double* out) {
 //   halo stream: 42 instead of 63 planes per step.  Opt-in (GFB200_HALO_SU3=1): measured +3 % at 64^4 on 2 GPUs with 8 slices
 //   each but -7 % on 8 GPUs (14 instead of 4 NCCL operations per step and one more kernel; the 8-GPU step is not
 //   bandwidth-bound) -- profiles/r1_tmarch.md.
+// ncclGroupStart/End pair that is closed on every return path
+struct NcclGroup {
+    bool open = false;
+    ncclResult_t start() { ncclResult_t r = ncclGroupStart(); open = (r == ncclSuccess); return r; }
+    ncclResult_t end() { open = false; return ncclGroupEnd(); }
+    ~NcclGroup() { if (open) ncclGroupEnd(); }
+};
 static int exchange_halo_buffers(gfb_ctx* ctx, const gfb_gauge* g, const std::vector<double2*>& buf, bool overlapped, bool su3 = false) {
     const int G = ctx->nslabs_total;
     if (G == 1) return GFB_OK;
@@ -154,7 +238,8 @@ static int exchange_halo_buffers(gfb_ctx* ctx, const gfb_gauge* g, const std::ve
             GFB_CUDA(ctx, cudaStreamWaitEvent(s.comm_stream, s.ev_a, 0));
         }
     }
-    GFB_NCCL(ctx, ncclGroupStart());
+    NcclGroup grp;
+    GFB_NCCL(ctx, grp.start());
     for (size_t i = 0; i < ctx->slabs.size(); i++) {
         Slab& s = ctx->slabs[i];
         cudaStream_t st = overlapped ? s.comm_stream : s.stream;
@@ -177,7 +262,7 @@ static int exchange_halo_buffers(gfb_ctx* ctx, const gfb_gauge* g, const std::ve
             for (int mu = 0; mu < 4; mu++) GFB_NCCL(ctx, ncclRecv(dn + mu * dir, rows01, ncclDouble, prev, s.nccl, st));
         }
     }
-    GFB_NCCL(ctx, ncclGroupEnd());
+    GFB_NCCL(ctx, grp.end());
     if (su3) {
         for (size_t i = 0; i < ctx->slabs.size(); i++) {
             Slab& s = ctx->slabs[i];
@@ -211,48 +296,89 @@ static int ensure_halo(gfb_gauge* g) {
     return GFB_OK;
 }
 
+// link buffers (one per local slab).  One process per GPU with peer halos: from the context's cache, and the ring neighbours'
+// buffers of the same collective call are mapped (PoolBuf::peer_prev/next).
 static int alloc_like(gfb_ctx* ctx, const gfb_gauge* g, std::vector<double2*>& out) {
     out.assign(ctx->slabs.size(), nullptr);
+    const size_t bytes = g->elems_per_slab() * sizeof(double2);
+    if (ctx->distributed && ctx->peer_ok) {
+        GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[0].device));
+        PoolBuf* pb = nullptr;
+        for (auto& b : ctx->pool)
+            if (!b.used && b.bytes == bytes) { pb = &b; break; }
+        if (!pb) {
+            PoolBuf nb;
+            GFB_CUDA(ctx, cudaMalloc(&nb.p, bytes));
+            nb.bytes = bytes;
+            ctx->pool.push_back(nb);
+            pb = &ctx->pool.back();
+        }
+        pb->used = true;
+        void *pp = nullptr, *pn = nullptr;
+        GFB_CHECK(exchange_ipc(ctx, pb->p, &pp, &pn));
+        pb->peer_prev = reinterpret_cast<double2*>(pp);
+        pb->peer_next = reinterpret_cast<double2*>(pn);
+        out[0] = reinterpret_cast<double2*>(pb->p);
+        return GFB_OK;
+    }
     for (size_t i = 0; i < ctx->slabs.size(); i++) {
         GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
-        GFB_CUDA(ctx, cudaMalloc(&out[i], g->elems_per_slab() * sizeof(double2)));
+        GFB_CUDA(ctx, cudaMalloc(&out[i], bytes));
     }
     return GFB_OK;
+}
+static void release_like(gfb_ctx* ctx, std::vector<double2*>& v) {
+    for (size_t i = 0; i < v.size(); i++) {
+        if (!v[i]) continue;
+        bool pooled = false;
+        for (auto& b : ctx->pool)
+            if (b.p == v[i]) { b.used = false; pooled = true; break; }
+        if (!pooled) { cudaSetDevice(ctx->slabs[i].device); cudaFree(v[i]); }
+    }
+    v.clear();
+}
+// the ring neighbours' copies of local buffer i of `bufs` (null when the halo goes over NCCL)
+static void peers_of(gfb_ctx* ctx, const std::vector<double2*>& bufs, size_t i, double2** prev, double2** next) {
+    *prev = *next = nullptr;
+    if (!ctx->peer_ok) return;
+    if (!ctx->distributed) {
+        const size_t n = bufs.size();
+        *prev = bufs[(i + n - 1) % n];
+        *next = bufs[(i + 1) % n];
+        return;
+    }
+    for (auto& b : ctx->pool)
+        if (b.p == bufs[i]) { *prev = b.peer_prev; *next = b.peer_next; return; }
 }
 
 }  // namespace gfb
 
 using namespace gfb;
 
-// workspaces owned by a gauge handle (double buffer for the fused updates, flow field Z)
-struct gfb_gauge_ws {
-    std::vector<double2*> alt;
-    std::vector<double*> z;
-};
-#include <unordered_map>
-static std::unordered_map<const gfb_gauge*, gfb_gauge_ws> g_ws;
-
+// workspaces owned by a gauge handle (double buffer for the fused updates, flow field Z): members of gfb_gauge
+typedef gfb_gauge gfb_gauge_ws;
 static int get_ws(gfb_gauge* g, bool need_alt, bool need_z, gfb_gauge_ws** out) {
     gfb_ctx* ctx = g->ctx;
-    gfb_gauge_ws& ws = g_ws[g];
-    if (need_alt && ws.alt.empty()) GFB_CHECK(alloc_like(ctx, g, ws.alt));
-    if (need_z && ws.z.empty()) {
-        ws.z.assign(ctx->slabs.size(), nullptr);
+    if (need_alt && g->alt.empty()) GFB_CHECK(alloc_like(ctx, g, g->alt));
+    if (need_z && g->z.empty()) {
+        g->z.assign(ctx->slabs.size(), nullptr);
         size_t n = (size_t)g->tloc * 32 * g->nx * g->ny * g->nz;
         for (size_t i = 0; i < ctx->slabs.size(); i++) {
             GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
-            GFB_CUDA(ctx, cudaMalloc(&ws.z[i], n * sizeof(double)));
+            GFB_CUDA(ctx, cudaMalloc(&g->z[i], n * sizeof(double)));
         }
     }
-    *out = &ws;
+    *out = g;
     return GFB_OK;
 }
-static void free_ws(gfb_gauge* g) {
-    auto it = g_ws.find(g);
-    if (it == g_ws.end()) return;
-    for (size_t i = 0; i < it->second.alt.size(); i++) { cudaSetDevice(g->ctx->slabs[i].device); cudaFree(it->second.alt[i]); }
-    for (size_t i = 0; i < it->second.z.size(); i++) { cudaSetDevice(g->ctx->slabs[i].device); cudaFree(it->second.z[i]); }
-    g_ws.erase(it);
+// device memory of a handle (the host struct stays)
+static void release_gauge_memory(gfb_gauge* g) {
+    gfb_ctx* ctx = g->ctx;
+    if (!ctx) return;
+    release_like(ctx, g->alt);
+    for (size_t i = 0; i < g->z.size(); i++) { cudaSetDevice(ctx->slabs[i].device); cudaFree(g->z[i]); }
+    g->z.clear();
+    release_like(ctx, g->d);
 }
 
 static bool same_shape(const gfb_gauge* a, const gfb_gauge* b) { return a->ctx == b->ctx && a->nx == b->nx && a->ny == b->ny && a->nz == b->nz && a->nt == b->nt; }
@@ -299,6 +425,7 @@ int gfb_init(int ngpu, const int* devices, gfb_ctx** out) {
         ncclResult_t r = ncclCommInitAll(comms.data(), ngpu, devs.data());
         if (r != ncclSuccess) { g_init_error = std::string("ncclCommInitAll: ") + ncclGetErrorString(r); delete ctx; return GFB_ERR_NCCL; }
         for (int i = 0; i < ngpu; i++) ctx->slabs[i].nccl = comms[i];
+        ctx->peer_ok = peer_halo_wanted() && setup_peers_local(ctx);
     }
     *out = ctx;
     return GFB_OK;
@@ -336,17 +463,41 @@ int gfb_init_rank(int rank, int nranks, const char* id128, int device, gfb_ctx**
         std::memcpy(&id, id128, 128);
         ncclResult_t r = ncclCommInitRank(&ctx->slabs[0].nccl, nranks, id, rank);
         if (r != ncclSuccess) { g_init_error = std::string("ncclCommInitRank: ") + ncclGetErrorString(r); delete ctx; return GFB_ERR_NCCL; }
+        ctx->peer_ok = peer_halo_wanted() && setup_peers_distributed(ctx);
+        ctx->err.clear();
     }
     *out = ctx;
     return GFB_OK;
 }
+
+static void release_field_memory(gfb_field* f);
+static void release_mom_memory(gfb_mom* p);
 
 int gfb_finalize(gfb_ctx* ctx) {
     if (!ctx) return GFB_OK;
     for (auto& s : ctx->slabs) {
         cudaSetDevice(s.device);
         cudaDeviceSynchronize();
+    }
+    // handles that outlive the context (host finalizers run in any order): release their device memory now and orphan them
+    for (gfb_field* f : ctx->fields) { release_field_memory(f); f->ctx = nullptr; f->parent = nullptr; }
+    for (gfb_gauge* g : ctx->gauges) { release_gauge_memory(g); g->ctx = nullptr; }
+    for (gfb_mom* p : ctx->moms) { release_mom_memory(p); p->ctx = nullptr; }
+    if (ctx->distributed && ctx->slabs[0].nccl && !ctx->ipc_opened.empty()) {
+        // nobody may free an exported buffer while a neighbour still maps it: close our mappings, meet, then free
+        Slab& s = ctx->slabs[0];
+        cudaSetDevice(s.device);
+        for (auto& kv : ctx->ipc_opened) cudaIpcCloseMemHandle(kv.second);
+        ctx->ipc_opened.clear();
+        if (ncclAllReduce(s.d_result, s.d_result, 1, ncclInt, ncclSum, s.nccl, s.stream) == ncclSuccess) cudaStreamSynchronize(s.stream);
+        cudaGetLastError();
+    }
+    for (auto& b : ctx->pool) { cudaSetDevice(ctx->slabs[0].device); cudaFree(b.p); }
+    ctx->pool.clear();
+    for (auto& s : ctx->slabs) {
+        cudaSetDevice(s.device);
         if (s.nccl) ncclCommDestroy(s.nccl);
+        if (s.d_flags) cudaFree(s.d_flags);
         if (s.d_partial) cudaFree(s.d_partial);
         if (s.d_result) cudaFree(s.d_result);
         if (s.h_result) cudaFreeHost(s.h_result);
@@ -365,6 +516,11 @@ int gfb_sync(gfb_ctx* ctx) {
         GFB_CUDA(ctx, cudaSetDevice(s.device));
         GFB_CUDA(ctx, cudaStreamSynchronize(s.stream));
         GFB_CUDA(ctx, cudaStreamSynchronize(s.comm_stream));
+        if (ctx->peer_ok) {
+            unsigned timed_out = 0;
+            GFB_CUDA(ctx, cudaMemcpy(&timed_out, s.d_flags + 2, sizeof(unsigned), cudaMemcpyDeviceToHost));
+            if (timed_out) return fail(ctx, GFB_ERR_NCCL, "halo exchange: a ring neighbour did not complete a pass within 20 s");
+        }
     }
     return GFB_OK;
 }
@@ -428,14 +584,20 @@ int gfb_gauge_alloc(gfb_ctx* ctx, int nx, int ny, int nz, int nt, gfb_gauge** ou
     g->has_halo = ctx->nslabs_total > 1;
     g->halo_valid = false;
     int st = alloc_like(ctx, g, g->d);
-    if (st != GFB_OK) { for (auto p : g->d) if (p) cudaFree(p); delete g; return st; }
+    if (st != GFB_OK) { release_like(ctx, g->d); delete g; return st; }
+    ctx->gauges.insert(g);
     *out = g;
     return GFB_OK;
 }
 int gfb_gauge_free(gfb_gauge* g) {
     if (!g) return GFB_OK;
-    free_ws(g);
-    for (size_t i = 0; i < g->d.size(); i++) { cudaSetDevice(g->ctx->slabs[i].device); cudaFree(g->d[i]); }
+    if (g->ctx) {  // null: the context was finalized first and has already released the device memory
+        // views of this configuration must not dangle
+        for (gfb_field* f : g->ctx->fields)
+            if (f->parent == g) { f->parent = nullptr; f->d.clear(); }
+        release_gauge_memory(g);
+        g->ctx->gauges.erase(g);
+    }
     delete g;
     return GFB_OK;
 }
@@ -452,12 +614,18 @@ int gfb_mom_alloc(gfb_ctx* ctx, int nx, int ny, int nz, int nt, gfb_mom** out) {
         GFB_CUDA(ctx, cudaMalloc(&p->d[i], p->elems_per_slab() * sizeof(double)));
         GFB_CUDA(ctx, cudaMemsetAsync(p->d[i], 0, p->elems_per_slab() * sizeof(double), ctx->slabs[i].stream));
     }
+    ctx->moms.insert(p);
     *out = p;
     return GFB_OK;
 }
+static void release_mom_memory(gfb_mom* p) {
+    if (!p->ctx) return;
+    for (size_t i = 0; i < p->d.size(); i++) { cudaSetDevice(p->ctx->slabs[i].device); cudaFree(p->d[i]); }
+    p->d.clear();
+}
 int gfb_mom_free(gfb_mom* p) {
     if (!p) return GFB_OK;
-    for (size_t i = 0; i < p->d.size(); i++) { cudaSetDevice(p->ctx->slabs[i].device); cudaFree(p->d[i]); }
+    if (p->ctx) { release_mom_memory(p); p->ctx->moms.erase(p); }
     delete p;
     return GFB_OK;
 }
@@ -479,6 +647,7 @@ int gfb_gauge_upload(gfb_gauge* g, int mu, const double* host) {
         GFB_CHECK(post_launch(ctx));
     }
     g->halo_valid = false;
+    g->unitary = -1;  // checked on first use by a fused pass (links_are_unitary)
     return GFB_OK;
 }
 int gfb_gauge_download(const gfb_gauge* g, int mu, double* host) {
@@ -518,6 +687,7 @@ int gfb_gauge_upload_ildg(gfb_gauge* g, const void* payload, int precision) {
         GFB_CHECK(post_launch(ctx));
     }
     g->halo_valid = false;
+    g->unitary = -1;  // a 32-bit file is unitary to 1e-7 only: the passes then use full 3x3 products unless gfb_reunitarize is called
     return GFB_OK;
 }
 int gfb_gauge_download_ildg(const gfb_gauge* g, void* payload, int precision) {
@@ -587,6 +757,7 @@ int gfb_gauge_copy(gfb_gauge* dst, const gfb_gauge* src) {
         GFB_CUDA(ctx, cudaMemcpyAsync(dst->d[i], src->d[i], src->elems_per_slab() * sizeof(double2), cudaMemcpyDeviceToDevice, ctx->slabs[i].stream));
     }
     dst->halo_valid = src->halo_valid;
+    dst->unitary = src->unitary;
     return GFB_OK;
 }
 int gfb_mom_copy(gfb_mom* dst, const gfb_mom* src) {
@@ -631,6 +802,7 @@ int gfb_set_cold(gfb_gauge* g) {
         GFB_CHECK(post_launch(ctx));
     }
     g->halo_valid = false;
+    g->unitary = 1;
     return GFB_OK;
 }
 int gfb_set_hot(gfb_gauge* g, uint64_t seed, int rng_alg) {
@@ -643,6 +815,7 @@ int gfb_set_hot(gfb_gauge* g, uint64_t seed, int rng_alg) {
         GFB_CHECK(post_launch(ctx));
     }
     g->halo_valid = false;
+    g->unitary = 1;
     return GFB_OK;
 }
 int gfb_gaussian_momenta(gfb_mom* p, uint64_t seed, uint64_t sweep, double sigma, int rng_alg) {
@@ -665,6 +838,7 @@ int gfb_reunitarize(gfb_gauge* g) {
         GFB_CHECK(post_launch(ctx));
     }
     g->halo_valid = false;
+    g->unitary = 1;
     return GFB_OK;
 }
 
@@ -767,7 +941,8 @@ int gfb_polyakov(gfb_gauge* g, double* out2) {
         }
         if (li >= 0) GFB_CHECK(ensure_staging(ctx, ctx->slabs[li], 2 * field * sizeof(double2)));
         if (r > 0 && (li >= 0 || lprev >= 0)) {
-            GFB_NCCL(ctx, ncclGroupStart());
+            NcclGroup grp;
+            GFB_NCCL(ctx, grp.start());
             if (lprev >= 0) {
                 Slab& sp = ctx->slabs[lprev];
                 GFB_NCCL(ctx, ncclSend(reinterpret_cast<double2*>(sp.d_staging) + field, field * 2, ncclDouble, r, sp.nccl, sp.stream));
@@ -776,7 +951,7 @@ int gfb_polyakov(gfb_gauge* g, double* out2) {
                 Slab& sr = ctx->slabs[li];
                 GFB_NCCL(ctx, ncclRecv(sr.d_staging, field * 2, ncclDouble, r - 1, sr.nccl, sr.stream));
             }
-            GFB_NCCL(ctx, ncclGroupEnd());
+            GFB_NCCL(ctx, grp.end());
         }
         if (li < 0) continue;
         Slab& s = ctx->slabs[li];
@@ -798,29 +973,75 @@ int gfb_polyakov(gfb_gauge* g, double* out2) {
 }
 
 // ---- updates -----------------------------------------------------------------------------------------
-// one fused pass over all local slabs: Z' = a*TA(U V^dag) + b*Z ; Uout = exp(c Z') Uin.
-// With several slabs and an output link field the pass is ordered boundary slices -> halo exchange of the OUTPUT
-// (halo stream) || interior slices -> join, so on return (in stream order) uout's halo slots are valid.
-static int fused_pass(gfb_gauge* g, const std::vector<double2*>& uin, const std::vector<double2*>* uout, const std::vector<double*>* zin,
-                      const std::vector<double*>* zout, const FusedArgs& fa) {
+// Are all links SU(3) to 1e-12?  The fused kernels form staples from two rows of their unitary factors (su3.cuh); a
+// configuration that came in through upload / ILDG / a written view is checked once (one read of U), and if it is not unitary
+// every pass on it uses full 3x3 products, like the reference's staples, which hold for any matrices.
+static int links_are_unitary(gfb_gauge* g, bool* yes) {
     gfb_ctx* ctx = g->ctx;
-    const bool split = ctx->nslabs_total > 1 && uout != nullptr;
-    auto launch = [&](size_t i, int t0, int tc, int stride = 1) -> int {
+    if (g->unitary < 0) {
+        for (size_t i = 0; i < ctx->slabs.size(); i++) {
+            Slab& s = ctx->slabs[i];
+            Geom geo = geom_of(g, i);
+            GFB_CHECK(ensure_partial(ctx, s, (size_t)plaquette_blocks(geo) * 2 + 16));
+            GFB_CUDA(ctx, cudaSetDevice(s.device));
+            int nb = 0;
+            launch_unitarity_defect(s.stream, geo, g->d[i], s.d_partial, &nb);
+            launch_final_max(s.stream, s.d_partial, nb, s.d_result);
+            GFB_CHECK(post_launch(ctx, 2));
+        }
+        double worst = 0.0;
+        GFB_CHECK(gather_scalars(ctx, 1, &worst, true));
+        g->unitary = (worst <= 1e-12) ? 1 : 0;
+    }
+    *yes = g->unitary == 1;
+    return GFB_OK;
+}
+
+// one fused pass over all local slabs: Z' = a*TA(U V^dag) + b*Z ; Uout = exp(c Z') Uin.
+// With several slabs and an output link field, on return (in stream order) uout's halo slots are valid:
+//   peer halos (default): the kernels store their boundary slices into the neighbours' halo slots themselves (NVLink peer
+//     stores, tmarch.cu / kernels.cu); one launch per slab, then one single-thread kernel that signals both ring neighbours and
+//     waits for their signal.  No pack, no send/recv kernel, no event chain, and the slab is not split.
+//   NCCL (GFB200_HALO=nccl or no peer access): boundary slices -> send/recv on the halo stream || interior slices -> join.
+static int fused_pass(gfb_gauge* g, const std::vector<double2*>& uin, const std::vector<double2*>* uout, const std::vector<double*>* zin,
+                      const std::vector<double*>* zout, FusedArgs fa) {
+    gfb_ctx* ctx = g->ctx;
+    bool unitary = true;
+    GFB_CHECK(links_are_unitary(g, &unitary));
+    fa.full3 = !unitary;
+    const bool slabs = ctx->nslabs_total > 1 && uout != nullptr;
+    auto launch = [&](size_t i, int t0, int tc, int stride, const FusedArgs& f) -> int {
         Slab& s = ctx->slabs[i];
         GFB_CUDA(ctx, cudaSetDevice(s.device));
         Geom geo = geom_of(g, i);
         geo.t_stride = stride;
         if (tc <= 0) return GFB_OK;
-        launch_force_fused(s.stream, geo, t0, tc, uin[i], uout ? (*uout)[i] : nullptr, zin ? (*zin)[i] : nullptr, zout ? (*zout)[i] : nullptr, fa);
+        launch_force_fused(s.stream, geo, t0, tc, uin[i], uout ? (*uout)[i] : nullptr, zin ? (*zin)[i] : nullptr, zout ? (*zout)[i] : nullptr, f);
         return post_launch(ctx);
     };
-    if (!split) {
-        for (size_t i = 0; i < ctx->slabs.size(); i++) GFB_CHECK(launch(i, 0, g->tloc));
+    if (!slabs) {
+        for (size_t i = 0; i < ctx->slabs.size(); i++) GFB_CHECK(launch(i, 0, g->tloc, 1, fa));
         return GFB_OK;
     }
-    for (size_t i = 0; i < ctx->slabs.size(); i++) GFB_CHECK(launch(i, 0, 2, g->tloc - 1));  // slices 0 and tloc-1 in one launch
-    GFB_CHECK(exchange_halo_buffers(ctx, g, *uout, true, true));  // unitary links: two rows travel
-    for (size_t i = 0; i < ctx->slabs.size(); i++) GFB_CHECK(launch(i, 1, g->tloc - 2));
+    if (ctx->peer_ok) {
+        const unsigned serial = ++ctx->pass_serial;
+        for (size_t i = 0; i < ctx->slabs.size(); i++) {
+            FusedArgs f = fa;
+            peers_of(ctx, *uout, i, &f.peer_prev, &f.peer_next);
+            if (!f.peer_prev || !f.peer_next) return fail(ctx, GFB_ERR_ARG, "internal: output buffer without peer mappings");
+            GFB_CHECK(launch(i, 0, g->tloc, 1, f));
+        }
+        for (auto& s : ctx->slabs) {
+            GFB_CUDA(ctx, cudaSetDevice(s.device));
+            launch_halo_signal_wait(s.stream, s.peer_flag_prev, s.peer_flag_next, s.d_flags, serial);
+            GFB_CHECK(post_launch(ctx));
+        }
+        return GFB_OK;
+    }
+    fa.leave_sms = true;
+    for (size_t i = 0; i < ctx->slabs.size(); i++) GFB_CHECK(launch(i, 0, 2, g->tloc - 1, fa));  // slices 0 and tloc-1 in one launch
+    GFB_CHECK(exchange_halo_buffers(ctx, g, *uout, true, unitary));  // unitary links: two rows may travel (GFB200_HALO_SU3)
+    for (size_t i = 0; i < ctx->slabs.size(); i++) GFB_CHECK(launch(i, 1, g->tloc - 2, 1, fa));
     return join_halo_exchange(ctx);
 }
 
@@ -892,6 +1113,7 @@ int gfb_exp_aF_U(gfb_gauge* w, double a, const gfb_mom* f, const gfb_gauge* u) {
         launch_update_links(ctx->slabs[i].stream, geom_of(w, i), 0, w->tloc, u->d[i], w->d[i], f->d[i], a);
         GFB_CHECK(post_launch(ctx));
     }
+    w->unitary = u->unitary;
     w->halo_valid = false;
     return GFB_OK;
 }
@@ -992,6 +1214,7 @@ int gfb_stout_forward(gfb_gauge* out, gfb_gauge* in, double rho, gfb_mom* q) {
     FusedArgs fa;
     fa.a = -rho; fa.c = 1.0; fa.do_exp = true; fa.write_z = (q != nullptr);
     GFB_CHECK(fused_pass(in, in->d, &out->d, nullptr, q ? &q->d : nullptr, fa));
+    out->unitary = in->unitary;
     out->halo_valid = true;
     return GFB_OK;
 }
@@ -1001,11 +1224,14 @@ int gfb_wilson_dSdU(gfb_gauge* d, gfb_gauge* g, double beta) {
     gfb_ctx* ctx = g->ctx;
     if (d == g || !same_shape(d, g)) return fail(ctx, GFB_ERR_ARG, "derivative field must be a distinct configuration of the same shape");
     GFB_CHECK(ensure_halo(g));
+    bool unitary = true;
+    GFB_CHECK(links_are_unitary(g, &unitary));
     for (size_t i = 0; i < ctx->slabs.size(); i++) {
         GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
-        launch_staple_field(ctx->slabs[i].stream, geom_of(g, i), g->d[i], d->d[i], beta / 2.0);
+        launch_staple_field(ctx->slabs[i].stream, geom_of(g, i), g->d[i], d->d[i], beta / 2.0, !unitary);
         GFB_CHECK(post_launch(ctx));
     }
+    d->unitary = 0;  // a derivative field, not a configuration
     d->halo_valid = false;
     return GFB_OK;
 }
@@ -1030,9 +1256,11 @@ int gfb_stout_backward(gfb_gauge* d_in, gfb_gauge* d_out, gfb_gauge* in, double 
     gfb_gauge_ws* ws = nullptr;
     GFB_CHECK(get_ws(d_in, true, false, &ws));  // Lambda = dS/dC lives in d_in's spare buffer (same layout, with halo slots)
     GFB_CHECK(ensure_halo(in));
+    bool unitary = true;
+    GFB_CHECK(links_are_unitary(in, &unitary));
     for (size_t i = 0; i < ctx->slabs.size(); i++) {
         GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
-        launch_stout_lambda(ctx->slabs[i].stream, geom_of(in, i), in->d[i], d_out->d[i], ws->alt[i], d_in->d[i], rho);
+        launch_stout_lambda(ctx->slabs[i].stream, geom_of(in, i), in->d[i], d_out->d[i], ws->alt[i], d_in->d[i], rho, !unitary);
         GFB_CHECK(post_launch(ctx));
     }
     GFB_CHECK(exchange_halo_buffers(ctx, d_in, ws->alt, false));  // neighbours' Lambda on the slab faces
@@ -1041,17 +1269,28 @@ int gfb_stout_backward(gfb_gauge* d_in, gfb_gauge* d_out, gfb_gauge* in, double 
         launch_stout_backward(ctx->slabs[i].stream, geom_of(in, i), in->d[i], ws->alt[i], d_in->d[i], rho);
         GFB_CHECK(post_launch(ctx));
     }
+    d_in->unitary = 0;
     d_in->halo_valid = false;
     return GFB_OK;
 }
 
 // ---- primitive table ------------------------------------------------------------------------------------
-static FieldRef ref_of(const gfb_field* f, size_t i) { return FieldRef{f->d[i], f->slice_planes()}; }
+static FieldRef ref_of(const gfb_field* f, size_t i) {
+    if (f->is_view) return FieldRef{f->parent->d[i] + (size_t)f->mu * 9 * f->nx * f->ny * f->nz, 36};
+    return FieldRef{f->d[i], 9};
+}
+// a view whose configuration was freed (or any handle whose context is gone) cannot be used any more
+static int check_field(const gfb_field* f) {
+    if (!f || !f->ctx) return fail(nullptr, GFB_ERR_ARG, "null or orphaned field handle");
+    if (f->is_view && !f->parent) return fail(f->ctx, GFB_ERR_ARG, "this view's gauge configuration has been freed");
+    return GFB_OK;
+}
+static const double2* plane0(const gfb_field* f) { return ref_of(f, 0).p; }
 static Geom geom_of(const gfb_field* f, size_t i) { return make_geom(f->ctx, f->nx, f->ny, f->nz, f->nt, f->ctx->slabs[i].index); }
 static bool same_shape(const gfb_field* a, const gfb_field* b) { return a->ctx == b->ctx && a->nx == b->nx && a->ny == b->ny && a->nz == b->nz && a->nt == b->nt; }
 static void mark_written(gfb_field* f) {
     f->halo_valid = false;
-    if (f->parent) f->parent->halo_valid = false;
+    if (f->parent) { f->parent->halo_valid = false; f->parent->unitary = -1; }
 }
 static bool is_zero(const Shift4& s) { return !s.v[0] && !s.v[1] && !s.v[2] && !s.v[3]; }
 static int read_shift(gfb_ctx* ctx, const int* shift4, Shift4* out) {
@@ -1065,20 +1304,21 @@ static int field_halo(gfb_field* f, const Shift4& s) {
     gfb_ctx* ctx = f->ctx;
     const int G = ctx->nslabs_total;
     if (G == 1 || s.v[3] == 0) return GFB_OK;
-    if (f->halo_valid && !f->parent) return GFB_OK;
+    if (f->halo_valid && !f->is_view) return GFB_OK;
     const size_t v3 = (size_t)f->nx * f->ny * f->nz;
     const size_t slice = (size_t)f->slice_planes() * v3 * 2, count = 9 * v3 * 2;  // doubles
-    GFB_NCCL(ctx, ncclGroupStart());
+    NcclGroup grp;
+    GFB_NCCL(ctx, grp.start());
     for (size_t i = 0; i < ctx->slabs.size(); i++) {
         Slab& sl = ctx->slabs[i];
         const int prev = (sl.index + G - 1) % G, next = (sl.index + 1) % G;
-        double* base = reinterpret_cast<double*>(f->d[i]);
+        double* base = reinterpret_cast<double*>(ref_of(f, i).p);
         GFB_NCCL(ctx, ncclSend(base, count, ncclDouble, prev, sl.nccl, sl.stream));
         GFB_NCCL(ctx, ncclSend(base + (size_t)(f->tloc - 1) * slice, count, ncclDouble, next, sl.nccl, sl.stream));
         GFB_NCCL(ctx, ncclRecv(base + (size_t)f->tloc * slice, count, ncclDouble, next, sl.nccl, sl.stream));
         GFB_NCCL(ctx, ncclRecv(base + (size_t)(f->tloc + 1) * slice, count, ncclDouble, prev, sl.nccl, sl.stream));
     }
-    GFB_NCCL(ctx, ncclGroupEnd());
+    GFB_NCCL(ctx, grp.end());
     f->halo_valid = true;
     return GFB_OK;
 }
@@ -1098,6 +1338,7 @@ int gfb_field_alloc(gfb_ctx* ctx, int nx, int ny, int nz, int nt, gfb_field** ou
         GFB_CUDA(ctx, cudaMalloc(&f->d[i], elems * sizeof(double2)));
         GFB_CUDA(ctx, cudaMemsetAsync(f->d[i], 0, elems * sizeof(double2), ctx->slabs[i].stream));
     }
+    ctx->fields.insert(f);
     *out = f;
     return GFB_OK;
 }
@@ -1106,21 +1347,26 @@ int gfb_field_view(gfb_gauge* g, int mu, gfb_field** out) {
     if (mu < 0 || mu > 3) return fail(g->ctx, GFB_ERR_ARG, "mu must be in 0..3");
     gfb_field* f = new gfb_field();
     f->ctx = g->ctx; f->nx = g->nx; f->ny = g->ny; f->nz = g->nz; f->nt = g->nt; f->tloc = g->tloc;
-    f->has_halo = g->has_halo; f->parent = g; f->mu = mu;
-    f->d.resize(g->d.size());
-    // note: the fused MD / flow passes swap the configuration's buffers; a view is valid until the next such call
-    for (size_t i = 0; i < g->d.size(); i++) f->d[i] = g->d[i] + (size_t)mu * 9 * g->nx * g->ny * g->nz;
+    f->has_halo = g->has_halo; f->parent = g; f->mu = mu; f->is_view = true;
+    // a view holds no pointers of its own: the fused MD / flow passes swap the configuration's buffers, so the planes are
+    // resolved from the parent at every use (ref_of)
+    g->ctx->fields.insert(f);
     *out = f;
     return GFB_OK;
 }
+static void release_field_memory(gfb_field* f) {
+    if (!f->ctx || f->is_view) return;
+    for (size_t i = 0; i < f->d.size(); i++) { cudaSetDevice(f->ctx->slabs[i].device); cudaFree(f->d[i]); }
+    f->d.clear();
+}
 int gfb_field_free(gfb_field* f) {
     if (!f) return GFB_OK;
-    if (!f->parent)
-        for (size_t i = 0; i < f->d.size(); i++) { cudaSetDevice(f->ctx->slabs[i].device); cudaFree(f->d[i]); }
+    if (f->ctx) { release_field_memory(f); f->ctx->fields.erase(f); }
     delete f;
     return GFB_OK;
 }
 static int field_transfer(gfb_field* f, double* host, bool to_host) {
+    GFB_CHECK(check_field(f));
     gfb_ctx* ctx = f->ctx;
     const size_t v3 = (size_t)f->nx * f->ny * f->nz;
     const size_t bytes = v3 * f->tloc * 9 * sizeof(double2);
@@ -1148,7 +1394,7 @@ int gfb_field_download(gfb_field* f, double* host) {
     return field_transfer(f, host, true);
 }
 static int field_fill(gfb_field* f, double diag) {
-    if (!f) return fail(nullptr, GFB_ERR_ARG, "null argument");
+    GFB_CHECK(check_field(f));
     gfb_ctx* ctx = f->ctx;
     for (size_t i = 0; i < ctx->slabs.size(); i++) {
         GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
@@ -1162,12 +1408,13 @@ int gfb_field_clear(gfb_field* f) { return field_fill(f, 0.0); }
 int gfb_field_unit(gfb_field* f) { return field_fill(f, 1.0); }
 
 static int axpy_impl(gfb_field* c, double2 alpha, gfb_field* a, const int* shift4, int dag, int assign) {
-    if (!c || !a) return fail(c ? c->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    GFB_CHECK(check_field(c));
+    GFB_CHECK(check_field(a));
     gfb_ctx* ctx = c->ctx;
     if (!same_shape(c, a)) return fail(ctx, GFB_ERR_ARG, "fields differ in shape");
     Shift4 s;
     GFB_CHECK(read_shift(ctx, shift4, &s));
-    if (!is_zero(s) && c->d[0] == a->d[0]) return fail(ctx, GFB_ERR_ARG, "a shifted source must not alias the destination");
+    if (!is_zero(s) && plane0(c) == plane0(a)) return fail(ctx, GFB_ERR_ARG, "a shifted source must not alias the destination");
     GFB_CHECK(field_halo(a, s));
     for (size_t i = 0; i < ctx->slabs.size(); i++) {
         GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
@@ -1182,13 +1429,15 @@ int gfb_axpy(gfb_field* c, double alpha_re, double alpha_im, gfb_field* a, int d
 
 int gfb_mul(gfb_field* c, gfb_field* a, const int* shift_a4, int dag_a, gfb_field* b, const int* shift_b4, int dag_b, double alpha_re, double alpha_im,
             double beta_re, double beta_im) {
-    if (!c || !a || !b) return fail(c ? c->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    GFB_CHECK(check_field(c));
+    GFB_CHECK(check_field(a));
+    GFB_CHECK(check_field(b));
     gfb_ctx* ctx = c->ctx;
     if (!same_shape(c, a) || !same_shape(c, b)) return fail(ctx, GFB_ERR_ARG, "fields differ in shape");
     Shift4 sa, sb;
     GFB_CHECK(read_shift(ctx, shift_a4, &sa));
     GFB_CHECK(read_shift(ctx, shift_b4, &sb));
-    if ((c->d[0] == a->d[0] && !is_zero(sa)) || (c->d[0] == b->d[0] && !is_zero(sb)))
+    if ((plane0(c) == plane0(a) && !is_zero(sa)) || (plane0(c) == plane0(b) && !is_zero(sb)))
         return fail(ctx, GFB_ERR_ARG, "the destination of mul! must not alias a shifted operand");
     GFB_CHECK(field_halo(a, sa));
     GFB_CHECK(field_halo(b, sb));
@@ -1202,7 +1451,9 @@ int gfb_mul(gfb_field* c, gfb_field* a, const int* shift_a4, int dag_a, gfb_fiel
     return GFB_OK;
 }
 static int trace_impl(gfb_field* a, gfb_field* b, double* out2) {
-    if (!a || !out2) return fail(a ? a->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    GFB_CHECK(check_field(a));
+    if (b) GFB_CHECK(check_field(b));
+    if (!out2) return fail(a->ctx, GFB_ERR_ARG, "null argument");
     gfb_ctx* ctx = a->ctx;
     if (b && !same_shape(a, b)) return fail(ctx, GFB_ERR_ARG, "fields differ in shape");
     for (size_t i = 0; i < ctx->slabs.size(); i++) {
@@ -1224,7 +1475,8 @@ int gfb_tr2(gfb_field* a, gfb_field* b, double* out2) {
     return trace_impl(a, b, out2);
 }
 static int ta_exp_impl(gfb_field* out, gfb_field* in, int mode, double t) {
-    if (!out || !in) return fail(out ? out->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    GFB_CHECK(check_field(out));
+    GFB_CHECK(check_field(in));
     gfb_ctx* ctx = out->ctx;
     if (!same_shape(out, in)) return fail(ctx, GFB_ERR_ARG, "fields differ in shape");
     if (!std::isfinite(t)) return fail(ctx, GFB_ERR_ARG, "t must be finite");
@@ -1239,7 +1491,8 @@ static int ta_exp_impl(gfb_field* out, gfb_field* in, int mode, double t) {
 int gfb_ta_project(gfb_field* q, gfb_field* m) { return ta_exp_impl(q, m, 0, 1.0); }
 int gfb_exp(gfb_field* e, double t, gfb_field* q) { return ta_exp_impl(e, q, 1, t); }
 static int mom_impl(gfb_field* f, gfb_mom* p, int mu, int mode, double s) {
-    if (!f || !p) return fail(f ? f->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    GFB_CHECK(check_field(f));
+    if (!p) return fail(f->ctx, GFB_ERR_ARG, "null argument");
     gfb_ctx* ctx = f->ctx;
     if (mu < 0 || mu > 3) return fail(ctx, GFB_ERR_ARG, "mu must be in 0..3");
     if (f->ctx != p->ctx || f->nx != p->nx || f->ny != p->ny || f->nz != p->nz || f->nt != p->nt) return fail(ctx, GFB_ERR_ARG, "fields differ in shape");

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <nccl.h>
 
+#include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -25,16 +27,45 @@ struct Slab {
     double* h_result = nullptr;   // pinned mirror
     void* d_staging = nullptr;    // AoS <-> SoA staging for upload/download
     size_t staging_cap = 0;
+    // t-slab halo by peer stores: flag words the neighbours write (their pass serial) and we spin on
+    //   d_flags[0] <- previous slab, d_flags[1] <- next slab, d_flags[2] = timeout marker
+    unsigned* d_flags = nullptr;
+    unsigned* peer_flag_prev = nullptr;  // previous slab's d_flags[1] (we are its next)
+    unsigned* peer_flag_next = nullptr;  // next slab's d_flags[0] (we are its previous)
+};
+
+// link buffers of a one-process-per-GPU context come from a per-context cache: they are exported to the two ring neighbours
+// (CUDA IPC) and are therefore never handed back to the driver before gfb_finalize (cudaFree of an exported allocation while
+// a neighbour still maps it is undefined); a released buffer is reused by the next request of the same size.
+struct PoolBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    bool used = false;
+    double2* peer_prev = nullptr;  // the previous / next slab's buffer allocated by the same collective call
+    double2* peer_next = nullptr;
 };
 
 }  // namespace gfb
 
+struct gfb_gauge;
+struct gfb_mom;
+struct gfb_field;
 struct gfb_ctx {
     std::vector<gfb::Slab> slabs;  // local slabs
     int nslabs_total = 1;
     bool distributed = false;  // one process per GPU
     std::string err;
     long long launches = 0;
+    // halo exchange by peer stores inside the fused kernels (api.cu, fused_pass); false -> NCCL send/recv
+    bool peer_ok = false;
+    unsigned pass_serial = 0;
+    std::vector<gfb::PoolBuf> pool;               // distributed contexts only
+    std::map<std::string, void*> ipc_opened;      // IPC handle bytes -> mapping in this process
+    // live handles: gfb_finalize releases their device memory and orphans them (ctx = nullptr), so that a handle freed after
+    // its context (finalizers run in any order in the Julia/Python hosts) only deletes the host struct
+    std::set<gfb_gauge*> gauges;
+    std::set<gfb_mom*> moms;
+    std::set<gfb_field*> fields;
 };
 
 struct gfb_gauge {
@@ -42,7 +73,12 @@ struct gfb_gauge {
     int nx = 0, ny = 0, nz = 0, nt = 0, tloc = 0;
     bool has_halo = false;
     bool halo_valid = false;
+    // 1: every link is SU(3) to 1e-12 (two-row products allowed), 0: not (full 3x3 products), -1: unknown (checked on first use)
+    int unitary = -1;
     std::vector<double2*> d;  // per local slab
+    // workspaces owned by the handle: double buffer of the fused updates, flow field Z
+    std::vector<double2*> alt;
+    std::vector<double*> z;
     size_t elems_per_slab() const { return (size_t)(tloc + (has_halo ? 2 : 0)) * 36 * (size_t)nx * ny * nz; }
     size_t slice_elems() const { return (size_t)36 * nx * ny * nz; }
 };
@@ -59,10 +95,11 @@ struct gfb_field {
     gfb_ctx* ctx = nullptr;
     int nx = 0, ny = 0, nz = 0, nt = 0, tloc = 0;
     bool has_halo = false, halo_valid = false;
-    gfb_gauge* parent = nullptr;  // non-null for views
+    gfb_gauge* parent = nullptr;  // views: the configuration (null once it has been freed)
+    bool is_view = false;
     int mu = 0;
-    std::vector<double2*> d;      // per local slab: pointer to plane 0 of slice 0 of this field
-    int slice_planes() const { return parent ? 36 : 9; }
+    std::vector<double2*> d;      // own buffers only (views resolve their planes from the parent at every use)
+    int slice_planes() const { return is_view ? 36 : 9; }
 };
 
 namespace gfb {
@@ -108,15 +145,22 @@ int fail(gfb_ctx* ctx, int code, const std::string& msg);
 struct FusedArgs {
     double a = 0, b = 0, c = 0;  // Z' = a*TA(U V^dag) + b*Z ; Uout = exp(c*Z') U
     bool read_z = false, write_z = false, do_exp = false;
+    // t-slab halo by peer stores: the neighbours' copies of the output link buffer, or null
+    double2* peer_prev = nullptr;
+    double2* peer_next = nullptr;
+    bool full3 = false;      // links not unitary to 1e-12: full 3x3 products (k_force_fused only, as the reference's staples)
+    bool leave_sms = false;  // NCCL-overlapped slab interior: one CTA per item instead of a persistent grid, so the send/recv kernels get SMs
 };
 void launch_force_fused(cudaStream_t st, const Geom& g, int t_begin, int t_count, const double2* uin, double2* uout, const double* zin, double* zout,
                         const FusedArgs& fa);
 // persistent t-marching shared-memory variant of launch_force_fused (tmarch.cu); false = launch not covered, nothing launched
 bool launch_tmarch_fused(cudaStream_t st, const Geom& g, int t_begin, int t_count, const double2* uin, double2* uout, const double* zin, double* zout,
                          const FusedArgs& fa);
-// persistent TMA row-tile variant of launch_force_fused (rowtile.cu); false = geometry not covered, nothing launched
-bool launch_rowtile_fused(cudaStream_t st, const Geom& g, int t_begin, int t_count, const double2* uin, double2* uout, const double* zin, double* zout,
-                          const FusedArgs& fa);
+// peer-store halo exchange: tell both ring neighbours that pass `serial` is complete here, then wait for theirs
+void launch_halo_signal_wait(cudaStream_t st, unsigned* peer_flag_prev, unsigned* peer_flag_next, unsigned* my_flags, unsigned serial);
+// max over the local links of |U U^dag - 1|_max and |det U - 1| -> partial[0..nblocks) (block maxima)
+void launch_unitarity_defect(cudaStream_t st, const Geom& g, const double2* u, double* partial, int* nblocks);
+void launch_final_max(cudaStream_t st, const double* partial, int n, double* out);
 void launch_update_links(cudaStream_t st, const Geom& g, int t_begin, int t_count, const double2* uin, double2* uout, const double* z, double c);
 void launch_plaquette(cudaStream_t st, const Geom& g, const double2* u, double* partial, int* nblocks);
 void launch_sumsq(cudaStream_t st, const double* p, size_t n, double* partial, int* nblocks);
@@ -139,9 +183,9 @@ void launch_reunitarize(cudaStream_t st, const Geom& g, double2* u);
 // rebuilds row 2 = conj(row0 x row1) of the links in the two halo slots (3 spatial directions in the t+1 slot, 4 in the t-1 slot)
 void launch_complete_su3_rows(cudaStream_t st, const Geom& g, double2* u);
 void launch_axpy(cudaStream_t st, double* y, double a, const double* x, size_t n);
-void launch_staple_field(cudaStream_t st, const Geom& g, const double2* u, double2* out, double scale);
+void launch_staple_field(cudaStream_t st, const Geom& g, const double2* u, double2* out, double scale, bool full3);
 void launch_kick_from_dsdu(cudaStream_t st, const Geom& g, const double2* u, const double2* d, double* p, double factor);
-void launch_stout_lambda(cudaStream_t st, const Geom& g, const double2* u, const double2* dout, double2* lambda, double2* din, double rho);
+void launch_stout_lambda(cudaStream_t st, const Geom& g, const double2* u, const double2* dout, double2* lambda, double2* din, double rho, bool full3);
 void launch_stout_backward(cudaStream_t st, const Geom& g, const double2* u, const double2* lambda, double2* din, double rho);
 
 }  // namespace gfb

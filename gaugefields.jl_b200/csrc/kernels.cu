@@ -31,10 +31,10 @@ namespace gfb {
 // step, the three RK3 flow stages (gradientflow.jl:192-226) and the stout forward layer
 // (stout_fast.jl:250-274).
 // ------------------------------------------------------------------------------------------------
-template <bool READ_Z, bool WRITE_Z, bool DO_EXP>
+template <bool READ_Z, bool WRITE_Z, bool DO_EXP, bool FULL3>
 __global__ void __launch_bounds__(128 * GFB_FF_ROWS, (GFB_FF_MINBLOCKS / GFB_FF_ROWS) > 0 ? (GFB_FF_MINBLOCKS / GFB_FF_ROWS) : 1)
 k_force_fused(Geom g, int t_begin, int t_count, const double2* __restrict__ uin, double2* __restrict__ uout, const double* __restrict__ zin,
-              double* __restrict__ zout, double a, double b, double c) {
+              double* __restrict__ zout, double a, double b, double c, double2* __restrict__ peer_prev, double2* __restrict__ peer_next) {
     const int mu = threadIdx.y;
     const long n = ((long)blockIdx.x * GFB_FF_ROWS + threadIdx.z) * blockDim.x + threadIdx.x;
 #if GFB_FF_L2PF > 0
@@ -63,7 +63,7 @@ k_force_fused(Geom g, int t_begin, int t_count, const double2* __restrict__ uin,
 #endif
     if (n >= (long)g.v3 * t_count) return;
     const Coord x = decode_site(g, n, t_begin, t_count);
-    M3 s = staple_sum(uin, g, x, mu);
+    M3 s = staple_sum<FULL3>(uin, g, x, mu);
     const M3 umu = load_link(uin, g, x, mu);
     double z[8];
     ta_coeffs_nd(umu, s, z);
@@ -77,8 +77,12 @@ k_force_fused(Geom g, int t_begin, int t_count, const double2* __restrict__ uin,
         if (WRITE_Z) *reinterpret_cast<double*>(reinterpret_cast<char*>(zout + zo) + (size_t)k * zsb) = v;
     }
     if (DO_EXP) {
-        const M3 r = exp_ta_times_su3(z, c, umu);
+        const M3 r = FULL3 ? mul_nn(exp_ta(z, c), umu) : exp_ta_times_su3(z, c, umu);
         store_link(uout, g, x, mu, r);
+        // t-slab halo by peer stores (same scheme as tmarch.cu): our boundary slices go straight into the neighbours' halo slots
+        const unsigned s3 = (unsigned)s3_of(g, x);
+        if (peer_prev != nullptr && x.t == 0 && mu < 3) m3_store(peer_prev + ((unsigned)(g.tloc * 36 + mu * 9) * (unsigned)g.v3 + s3), (unsigned)g.v3, r);
+        if (peer_next != nullptr && x.t == g.tloc - 1) m3_store(peer_next + ((unsigned)((g.tloc + 1) * 36 + mu * 9) * (unsigned)g.v3 + s3), (unsigned)g.v3, r);
     }
 }
 
@@ -88,10 +92,15 @@ void launch_force_fused(cudaStream_t st, const Geom& g, int t_begin, int t_count
     dim3 block(32, 4, GFB_FF_ROWS);
     long nsites = (long)g.v3 * t_count;
     if (nsites <= 0) return;
-    if (launch_tmarch_fused(st, g, t_begin, t_count, uin, uout, zin, zout, fa)) return;
-    if (launch_rowtile_fused(st, g, t_begin, t_count, uin, uout, zin, zout, fa)) return;
+    if (!fa.full3 && launch_tmarch_fused(st, g, t_begin, t_count, uin, uout, zin, zout, fa)) return;
     dim3 grid((unsigned)((nsites + SITES - 1) / SITES));
-#define GFB_LAUNCH_FF(R, W, E) k_force_fused<R, W, E><<<grid, block, 0, st>>>(g, t_begin, t_count, uin, uout, zin, zout, fa.a, fa.b, fa.c)
+    double2* const pp = fa.do_exp ? fa.peer_prev : nullptr;
+    double2* const pn = fa.do_exp ? fa.peer_next : nullptr;
+#define GFB_LAUNCH_FF(R, W, E)                                                                                                       \
+    do {                                                                                                                             \
+        if (fa.full3) k_force_fused<R, W, E, true><<<grid, block, 0, st>>>(g, t_begin, t_count, uin, uout, zin, zout, fa.a, fa.b, fa.c, pp, pn);  \
+        else k_force_fused<R, W, E, false><<<grid, block, 0, st>>>(g, t_begin, t_count, uin, uout, zin, zout, fa.a, fa.b, fa.c, pp, pn);          \
+    } while (0)
     if (fa.read_z) {
         if (fa.do_exp) GFB_LAUNCH_FF(true, true, true);
         else GFB_LAUNCH_FF(true, true, false);
@@ -322,6 +331,86 @@ void launch_complete_su3_rows(cudaStream_t st, const Geom& g, double2* u) {
     const long n = 7L * g.v3;
     k_complete_su3_rows<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, u);
 }
+
+// ------------------------------------------------------------------------------------------------
+// t-slab halo exchange by peer stores: after a fused pass every rank tells its two ring neighbours "pass `serial` is complete
+// here" (its boundary slices already sit in their halo slots: the pass stored them there) and waits for theirs.  One thread;
+// runs in stream order behind the pass, so the kernel boundary has made the pass's peer stores visible system-wide before the
+// flag is written.  The spin is bounded (about 20 s): a dead neighbour must not hang the GPU; d_flags[2] records the timeout
+// and the host turns it into an error at the next synchronising call.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_halo_signal_wait(unsigned* peer_flag_prev, unsigned* peer_flag_next, unsigned* my_flags, unsigned serial) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flag_prev), "r"(serial) : "memory");
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flag_next), "r"(serial) : "memory");
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        unsigned a, b;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(a) : "l"(my_flags) : "memory");
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(b) : "l"(my_flags + 1) : "memory");
+        if ((int)(a - serial) >= 0 && (int)(b - serial) >= 0) break;
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 20000000000ull) { my_flags[2] = serial; break; }
+        __nanosleep(200);
+    }
+}
+void launch_halo_signal_wait(cudaStream_t st, unsigned* peer_flag_prev, unsigned* peer_flag_next, unsigned* my_flags, unsigned serial) {
+    k_halo_signal_wait<<<1, 1, 0, st>>>(peer_flag_prev, peer_flag_next, my_flags, serial);
+}
+
+// how far the links are from SU(3): max over the 9 entries of |U U^dag - 1| and |det U - 1| (two-row products need 1e-12)
+__global__ void __launch_bounds__(128) k_unitarity_defect(Geom g, const double2* __restrict__ u, double* __restrict__ partial) {
+    const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    double worst = 0.0;
+    if (n < (long)g.v3 * g.tloc) {
+        const Coord x = decode_site(g, n, 0, g.tloc);
+#pragma unroll 1
+        for (int mu = 0; mu < 4; mu++) {
+            const M3 a = load_link(u, g, x, mu);
+            M3 w = mul_nd(a, a);
+            w.e[0].x -= 1.0; w.e[4].x -= 1.0; w.e[8].x -= 1.0;
+#pragma unroll
+            for (int k = 0; k < 9; k++) worst = fmax(worst, fmax(fabs(w.e[k].x), fabs(w.e[k].y)));
+            // det = row0 . (row1 x row2)
+            double2 c0 = cmul(a.e[4], a.e[8]); { const double2 v = cmul(a.e[5], a.e[7]); c0.x -= v.x; c0.y -= v.y; }
+            double2 c1 = cmul(a.e[5], a.e[6]); { const double2 v = cmul(a.e[3], a.e[8]); c1.x -= v.x; c1.y -= v.y; }
+            double2 c2 = cmul(a.e[3], a.e[7]); { const double2 v = cmul(a.e[4], a.e[6]); c2.x -= v.x; c2.y -= v.y; }
+            double2 det = cmul(a.e[0], c0);
+            cmac(det, a.e[1], c1);
+            cmac(det, a.e[2], c2);
+            worst = fmax(worst, fmax(fabs(det.x - 1.0), fabs(det.y)));
+            if (!(worst == worst)) worst = 1e300;  // NaN links are not unitary
+        }
+    }
+    __shared__ double wp[4];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) worst = fmax(worst, __shfl_down_sync(0xffffffffu, worst, o));
+    if ((threadIdx.x & 31) == 0) wp[threadIdx.x >> 5] = worst;
+    __syncthreads();
+    if (threadIdx.x == 0) partial[blockIdx.x] = fmax(fmax(wp[0], wp[1]), fmax(wp[2], wp[3]));
+}
+void launch_unitarity_defect(cudaStream_t st, const Geom& g, const double2* u, double* partial, int* nblocks) {
+    const int nb = plaquette_blocks(g);
+    k_unitarity_defect<<<nb, 128, 0, st>>>(g, u, partial);
+    *nblocks = nb;
+}
+__global__ void __launch_bounds__(1024) k_final_max(const double* __restrict__ partial, int n, double* __restrict__ out) {
+    double m = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, partial[i]);
+    __shared__ double wp[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) wp[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r = 0.0;
+        for (int i = 0; i < 32; i++) r = fmax(r, wp[i]);
+        *out = r;
+    }
+}
+void launch_final_max(cudaStream_t st, const double* partial, int n, double* out) { k_final_max<<<1, 1024, 0, st>>>(partial, n, out); }
 
 // ------------------------------------------------------------------------------------------------
 // host layout <-> device layout.  staging holds this slab's chunk of the reference's gathered array
@@ -573,21 +662,23 @@ void launch_axpy(cudaStream_t st, double* y, double a, const double* x, size_t n
 // ------------------------------------------------------------------------------------------------
 // out_mu(x) = scale * sum of the six staples A with tr(loop) = tr(U_mu A), i.e. scale * V_mu(x)^dagger
 // (calc_dSdUmu!, GaugeActions.jl:95-123 for the plaquette+plaquette' action with scale = beta/2)
+template <bool FULL3>
 __global__ void __launch_bounds__(128, 3) k_staple_field(Geom g, const double2* __restrict__ u, double2* __restrict__ out, double scale) {
     const int mu = threadIdx.y;
     const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= (long)g.v3 * g.tloc) return;
     const Coord x = decode_site(g, n, 0, g.tloc);
-    M3 s = staple_sum(u, g, x, mu);
+    M3 s = staple_sum<FULL3>(u, g, x, mu);
     M3 d = m3_dagger(s);
 #pragma unroll
     for (int k = 0; k < 9; k++) { d.e[k].x *= scale; d.e[k].y *= scale; }
     store_link(out, g, x, mu, d);
 }
-void launch_staple_field(cudaStream_t st, const Geom& g, const double2* u, double2* out, double scale) {
+void launch_staple_field(cudaStream_t st, const Geom& g, const double2* u, double2* out, double scale, bool full3) {
     dim3 block(32, 4);
     long nsites = (long)g.v3 * g.tloc;
-    k_staple_field<<<(unsigned)((nsites + 31) / 32), block, 0, st>>>(g, u, out, scale);
+    if (full3) k_staple_field<true><<<(unsigned)((nsites + 31) / 32), block, 0, st>>>(g, u, out, scale);
+    else k_staple_field<false><<<(unsigned)((nsites + 31) / 32), block, 0, st>>>(g, u, out, scale);
 }
 
 // P_mu += factor * TAcoeffs(U_mu * D_mu)  (md_force! tail, molecular_dynamics.jl:255-265)

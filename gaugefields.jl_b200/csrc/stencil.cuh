@@ -106,9 +106,19 @@ __device__ __forceinline__ void accumulate_staple(M3& s, const StapleOps& o, int
     }
 }
 
+// FULL3 = true: generic 3x3 products for links that are not (yet) unitary -- exactly the reference's staples
+template <bool FULL3 = false>
 __device__ __forceinline__ M3 staple_sum(const double2* __restrict__ u, const Geom& g, const Coord& x, int mu) {
     M3 s = m3_zero();
     const Coord xm = step(g, x, mu, +1);
+    if (FULL3) {
+#pragma unroll 1
+        for (int j = 0; j < 6; j++) {
+            const StapleOps o = fetch_staple(u, g, x, xm, mu, j);
+            accumulate_staple(s, o, j);
+        }
+        return s;
+    }
 #if GFB_FF_PIPE == 1
 #pragma unroll 1
     for (int j = 0; j < 6; j++) {

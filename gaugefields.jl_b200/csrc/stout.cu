@@ -94,13 +94,14 @@ __device__ __forceinline__ M3 exp_pullback(const M3& cm, const double* q) {
 }
 
 // kernel 1: site-local part of the pull-back and Lambda = dS/dC
+template <bool FULL3>
 __global__ void __launch_bounds__(128, 2)
 k_stout_local(Geom g, const double2* __restrict__ u, const double2* __restrict__ dout, double2* __restrict__ lambda, double2* __restrict__ din, double rho) {
     const int mu = threadIdx.y;
     const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= (long)g.v3 * g.tloc) return;
     const Coord x = decode_site(g, n, 0, g.tloc);
-    M3 c = staple_sum(u, g, x, mu);  // V_mu
+    M3 c = staple_sum<FULL3>(u, g, x, mu);  // V_mu
     const M3 umu = load_link(u, g, x, mu);
     double q[8];
     {
@@ -190,10 +191,11 @@ k_stout_gather(Geom g, const double2* __restrict__ u, const double2* __restrict_
     m3_store(din + off, (unsigned)g.v3, d);
 }
 
-void launch_stout_lambda(cudaStream_t st, const Geom& g, const double2* u, const double2* dout, double2* lambda, double2* din, double rho) {
+void launch_stout_lambda(cudaStream_t st, const Geom& g, const double2* u, const double2* dout, double2* lambda, double2* din, double rho, bool full3) {
     dim3 block(32, 4);
     long nsites = (long)g.v3 * g.tloc;
-    k_stout_local<<<(unsigned)((nsites + 31) / 32), block, 0, st>>>(g, u, dout, lambda, din, rho);
+    if (full3) k_stout_local<true><<<(unsigned)((nsites + 31) / 32), block, 0, st>>>(g, u, dout, lambda, din, rho);
+    else k_stout_local<false><<<(unsigned)((nsites + 31) / 32), block, 0, st>>>(g, u, dout, lambda, din, rho);
 }
 void launch_stout_backward(cudaStream_t st, const Geom& g, const double2* u, const double2* lambda, double2* din, double rho) {
     dim3 block(32, 4);

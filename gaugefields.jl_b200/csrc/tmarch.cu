@@ -29,11 +29,14 @@
 #include "stencil.cuh"
 #include "tmarch_geom.h"
 
-#ifndef GFB_TM_UNIFORM_ISSUE
-#define GFB_TM_UNIFORM_ISSUE 0  // 1: one elected thread issues all tensor copies back to back from uniform operands (box table in constant memory); measured 32^4 0.654 ms vs 0.620, 64^4 10.33 vs 10.38: not adopted
+#ifndef GFB_TM_PIPE
+#define GFB_TM_PIPE 0  // 1: operands requested one product ahead in program order (tm_step)
+#endif
+#ifndef GFB_TM_PREGS
+#define GFB_TM_PREGS 24  // registers per producer-group thread; the consumers get (64512 - 128*PREGS)/256 rounded down to 8
 #endif
 #ifndef GFB_TM_DEBUG
-#define GFB_TM_DEBUG 0  // 1: no staple arithmetic (copies + operand reads only); 2: no global->shared copies (barriers only; arithmetic on stale smem)
+#define GFB_TM_DEBUG 0  // 1: no staple arithmetic (copies + operand reads only); 2: no global->shared copies (barriers only; arithmetic on stale smem); 3: no shared-memory reads (arithmetic on fabricated operands)
 #endif
 
 namespace gfb {
@@ -100,7 +103,13 @@ struct SmOp {
 };
 __device__ __forceinline__ double2 lds_el(const SmOp& o, int k) {
     double2 v;
+#if GFB_TM_DEBUG == 3  // diagnostic: no shared-memory reads at all; operands fabricated in registers (one conversion + one add each)
+    const unsigned a = o.p + k * o.stride;  // doubles in [0.25, 0.5) built with integer instructions only (no FP64-pipe work added)
+    v.x = __hiloint2double(0x3FD00000 | (a & 0xFFFF), a);
+    v.y = __hiloint2double(0x3FD00000 | ((a >> 4) & 0xFFFF), ~a);
+#else
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(o.p + k * o.stride));
+#endif
     return v;
 }
 __device__ __forceinline__ M3 lds_m3(const SmOp& o) {
@@ -129,25 +138,209 @@ __device__ __forceinline__ R2 lds_dag_rows01(const SmOp& o) {
 }
 __device__ __forceinline__ int wrap(int c, int n) { return c < 0 ? c + n : (c >= n ? c - n : c); }
 
-// The whole persistent loop of one link-thread.  mu is warp-uniform but NOT a template parameter: all eight warps run the same
-// instructions (a per-direction instantiation made the straight-line staple code four times larger than the instruction
-// cache could hold: "no instruction" was the top stall of the first version, profiles/r1_tmarch.md).
+// What a fused pass needs besides the lattice: field pointers, the coefficients of Z' = a TA(U V^dag) + b Z, U' = exp(c Z') U,
+// the swizzle mask of the tile boxes (0x70 with CU_TENSOR_MAP_SWIZZLE_128B maps, 0 with linear ones) and -- on a t-slab
+// decomposition -- the neighbours' copies of the OUTPUT link buffer: the boundary slices of U' are stored to the neighbours'
+// halo slots by the threads that compute them (peer stores over NVLink inside the compute kernel; no pack, no send/recv kernel).
+struct TmArgs {
+    const double2* uin;
+    double2* uout;
+    const double* zin;
+    double* zout;
+    double a, b, c;
+    unsigned swz;
+    double2* peer_prev;  // previous slab's output buffer: our slice 0 (spatial links) goes to its slot tloc
+    double2* peer_next;  // next slab's output buffer: our slice tloc-1 (all links) goes to its slot tloc+1
+};
+
+// item -> (tile origin, t-segment)
+struct TmItem {
+    int x0, y0, z0, tb, len;
+};
+__device__ __forceinline__ TmItem decode_item(const TmPlan& pl, long item) {
+    TmItem it;
+    const int seg = (int)(item / pl.ntiles);
+    int tile = (int)(item % pl.ntiles);
+    it.x0 = (tile % pl.ntx) * tm::BX; tile /= pl.ntx;
+    it.y0 = (tile % pl.nty) * tm::BY;
+    it.z0 = (tile / pl.nty) * tm::BZ;
+    it.tb = pl.t_begin + seg * pl.seg_len;
+    it.len = min(pl.seg_len, pl.t_begin + pl.t_count - it.tb);
+    return it;
+}
+
+// One slice step of one link-thread: the six staples from shared memory (the backward-t staple G is carried), the TA force,
+// Z' and U' = exp(c Z') U.  `release` is called once every shared-memory operand of the step has been consumed.
+template <bool READ_Z, bool WRITE_Z, bool DO_EXP, class Release>
+__device__ __forceinline__ void tm_step(const int MU, const Geom& g, const TmArgs& ar, const int* od, const int t, const unsigned s3, const unsigned sc,
+                                        const unsigned d_r, const unsigned d_n, R2& G, Release release) {
+    auto at = [&](int d) -> SmOp {
+        SmOp o;
+        o.p = sc + ((unsigned)d & 0xFFFFu) + (((unsigned)d >> 28) & 1u) * d_r + (((unsigned)d >> 29) & 1u) * d_n;
+        o.p ^= (o.p >> 3) & ((((unsigned)d >> 30) & 1u) * ar.swz);  // 128-byte swizzle of the tile boxes (tmarch_geom.h, lookup())
+        o.stride = (((unsigned)d >> 16) & 0xFFu) * 16u;
+        return o;
+    };
+    const unsigned zo = (unsigned)(t * 32 + MU * 8) * (unsigned)g.v3 + s3;
+    const unsigned zsb = (unsigned)g.v3 * 8u;
+    double z[8];
+    if (READ_Z) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) z[k] = __ldg(reinterpret_cast<const double*>(reinterpret_cast<const char*>(ar.zin + zo) + (size_t)k * zsb));
+    }
+
+    M3 V, U;
+    if (MU < 3) V = complete_su3(G);
+    else V = m3_zero();
+#if GFB_TM_DEBUG == 1
+#pragma unroll
+    for (int jj = 0; jj < 3; jj++) {
+        m3_add(V, lds_m3(at(od[1 + 6 * jj]))); m3_add(V, lds_m3(at(od[2 + 6 * jj]))); m3_add(V, lds_m3(at(od[3 + 6 * jj])));
+        if (jj < 2 || MU == 3) { m3_add(V, lds_m3(at(od[4 + 6 * jj]))); m3_add(V, lds_m3(at(od[5 + 6 * jj]))); m3_add(V, lds_m3(at(od[6 + 6 * jj]))); }
+    }
+    U = lds_m3(at(od[0]));
+#elif GFB_TM_PIPE
+    // Software pipeline in PROGRAM order (the loads are volatile asm, which ptxas keeps in order): every operand is requested one
+    // whole 72-FMA product before its first use -- C of staple s ahead of T = A B, A and B of staple s+1 ahead of R = T C -- so
+    // that with two warps per scheduler a warp does not sit on the short scoreboard a few FMAs after each LDS.  Live registers:
+    // V 36 + T 24 + R 24 + C 36 + A' 24 + B' 36 + addressing ~45 = ~225 (the backward staple G is dead here, z comes later).
+    {
+        // staple s = 0..3: (upper, lower) of the two spatial-or-first directions; descriptors 1+6j.. (upper A,B,C), 4+6j.. (lower)
+        R2 A = lds_rows01(at(od[1]));
+        M3 B = lds_m3(at(od[2]));
+#pragma unroll
+        for (int s4 = 0; s4 < 4; s4++) {
+            const int jj = s4 >> 1, lo = s4 & 1;
+            const M3 C = lds_m3(at(od[(lo ? 6 : 3) + 6 * jj]));
+            const R2 T = r2_mul_nn(A, B);
+            M3 Bn;
+            R2 An;
+            M3 Afull;  // s4 == 3: operand 13 is needed in full by the nu = t tail of a spatial link
+            if (s4 < 3) {
+                const int s5 = s4 + 1, j2 = s5 >> 1, l2 = s5 & 1;
+                An = l2 ? lds_dag_rows01(at(od[4 + 6 * j2])) : lds_rows01(at(od[1 + 6 * j2]));
+                Bn = lds_m3(at(od[(l2 ? 5 : 2) + 6 * j2]));
+            } else {
+                Afull = lds_m3(at(od[13]));
+                Bn = lds_m3(at(od[14]));
+                An = rows01(Afull);
+            }
+            acc_su3(V, lo ? r2_mul_nn(T, C) : r2_mul_nd(T, C));
+            if (s4 == 3) {
+                if (MU == 3) {
+                    // upper(2), lower(2) of a t-link: same pipeline, two more staples, then the own link
+                    const M3 C2 = lds_m3(at(od[15]));
+                    const R2 T2 = r2_mul_nn(An, Bn);
+                    const R2 A3 = lds_dag_rows01(at(od[16]));
+                    const M3 B3 = lds_m3(at(od[17]));
+                    acc_su3(V, r2_mul_nd(T2, C2));
+                    const M3 C3 = lds_m3(at(od[18]));
+                    const R2 T3 = r2_mul_nn(A3, B3);
+                    U = lds_m3(at(od[0]));
+                    acc_su3(V, r2_mul_nn(T3, C3));
+                } else {
+                    // nu = t: the upper staple U_t(x) U_mu(x+t) U_t(x+mu)^dag and the NEXT slice's backward staple
+                    // U_t(x)^dag U_mu(x) U_t(x+mu) share A = U_t(x) and C = U_t(x+mu); B of the latter is the own link
+                    const M3 Ct = lds_m3(at(od[15]));
+                    const R2 T2 = r2_mul_nn(An, Bn);
+                    U = lds_m3(at(od[0]));
+                    acc_su3(V, r2_mul_nd(T2, Ct));
+                    const R2 T3 = r2_mul_nn(rows01_dag(Afull), U);
+                    G = r2_mul_nn(T3, Ct);
+                }
+            }
+            A = An;
+            B = Bn;
+        }
+    }
+#else
+    auto upper = [&](int jj) {  // A B C^dag
+        const R2 A = lds_rows01(at(od[1 + 6 * jj]));
+        const M3 B = lds_m3(at(od[2 + 6 * jj]));
+        const R2 T = r2_mul_nn(A, B);
+        const M3 C = lds_m3(at(od[3 + 6 * jj]));
+        acc_su3(V, r2_mul_nd(T, C));
+    };
+    auto lower = [&](int jj) {  // A^dag B C
+        const R2 A = lds_dag_rows01(at(od[4 + 6 * jj]));
+        const M3 B = lds_m3(at(od[5 + 6 * jj]));
+        const R2 T = r2_mul_nn(A, B);
+        const M3 C = lds_m3(at(od[6 + 6 * jj]));
+        acc_su3(V, r2_mul_nn(T, C));
+    };
+    upper(0); lower(0);
+    upper(1); lower(1);
+    if (MU == 3) {
+        upper(2); lower(2);
+        U = lds_m3(at(od[0]));
+    } else {
+        // nu = t: the upper staple U_t(x) U_mu(x+t) U_t(x+mu)^dag and the NEXT slice's backward staple
+        // U_t(x)^dag U_mu(x) U_t(x+mu) share A = U_t(x) and C = U_t(x+mu); B of the latter is the own link
+        const M3 A = lds_m3(at(od[13]));
+        const M3 C = lds_m3(at(od[15]));
+        {
+            const M3 B = lds_m3(at(od[14]));
+            const R2 T = r2_mul_nn(rows01(A), B);
+            acc_su3(V, r2_mul_nd(T, C));
+        }
+        U = lds_m3(at(od[0]));
+        const R2 T = r2_mul_nn(rows01_dag(A), U);
+        G = r2_mul_nn(T, C);
+    }
+#endif
+
+    double f[8];
+    ta_coeffs_nd(U, V, f);
+    release();
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        double v = ar.a * f[k];
+        if (READ_Z) v = fma(ar.b, z[k], v);
+        f[k] = v;
+        if (WRITE_Z) *reinterpret_cast<double*>(reinterpret_cast<char*>(ar.zout + zo) + (size_t)k * zsb) = v;
+    }
+    if (DO_EXP) {
+        const M3 r = exp_ta_times_su3(f, ar.c, U);
+        const unsigned uo = (unsigned)(t * 36 + MU * 9) * (unsigned)g.v3 + s3;
+        m3_store(ar.uout + uo, (unsigned)g.v3, r);
+        // t-slab halo: the neighbours' halo slots are filled from here (slot tloc = their t+1 halo needs our slice 0's three
+        // spatial links, slot tloc+1 = their t-1 halo needs our last slice's four links; SURVEY 8e, set_wing_U! in the reference)
+        if (ar.peer_prev != nullptr && t == 0 && MU < 3)
+            m3_store(ar.peer_prev + ((unsigned)(g.tloc * 36 + MU * 9) * (unsigned)g.v3 + s3), (unsigned)g.v3, r);
+        if (ar.peer_next != nullptr && t == g.tloc - 1)
+            m3_store(ar.peer_next + ((unsigned)((g.tloc + 1) * 36 + MU * 9) * (unsigned)g.v3 + s3), (unsigned)g.v3, r);
+    }
+}
+
+// backward-t staple of the first slice of a segment, from global memory (afterwards it is carried in registers)
+__device__ __forceinline__ R2 first_backward_staple(const int MU, const Geom& g, const double2* __restrict__ uin, const Coord& x) {
+    const Coord y = step(g, x, 3, -1);
+    const Coord ym = step(g, y, MU, +1);
+    const M3 A = load_link(uin, g, y, 3);
+    const M3 U = load_link(uin, g, y, MU);
+    const M3 C = load_link(uin, g, ym, 3);
+    return r2_mul_nn(r2_mul_nn(rows01_dag(A), U), C);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Variant A (GFB200_TMARCH_WS=0): 8 warps, warp 0 also issues the copies, one CTA-wide barrier per slice step.
+// mu is warp-uniform but NOT a template parameter: all eight warps run the same instructions (a per-direction instantiation
+// made the straight-line staple code four times larger than the instruction cache could hold, profiles/r1_tmarch.md).
+// ---------------------------------------------------------------------------------------------------------------------
 template <bool READ_Z, bool WRITE_Z, bool DO_EXP>
-__device__ __forceinline__ void tm_run(const int MU, const TmMaps& maps, const Geom& g, const TmPlan& pl, const double2* __restrict__ uin,
-                                       double2* __restrict__ uout, const double* __restrict__ zin, double* __restrict__ zout, double a, double b,
-                                       double c, unsigned char* smem, uint64_t* bars, const tm::Tables* __restrict__ tab) {
+__device__ __forceinline__ void tm_run(const int MU, const TmMaps& maps, const Geom& g, const TmPlan& pl, const TmArgs& ar, unsigned char* smem,
+                                       uint64_t* bars, const tm::Tables* __restrict__ tab) {
     const int tid = threadIdx.x;
     const int sidx = tid & (tm::SITES - 1);
     const int sx = sidx & (tm::BX - 1), sy = (sidx / tm::BX) & (tm::BY - 1), sz = sidx / (tm::BX * tm::BY);
     unsigned char* const sS = smem;
-    unsigned char* const sR = smem + tm::S_RING * tm::S_BYTES;
+    unsigned char* const sR = smem + tm::S_RING * tm::S_SLOT;
 
     // ---- consumer side: operand descriptors (tile independent; tm::make_descriptors, tabulated once on the host)
     int od[tm::NDESC];
 #pragma unroll
     for (int i = 0; i < tm::NDESC; i++) od[i] = tab->desc[i][tid];
 
-#if !GFB_TM_UNIFORM_ISSUE
     // ---- producer side: lane b of warp 0 owns box b (21 boxes per slice)
     const bool is_producer = tid < tm::NBOX;
     int bx_o[3] = {0, 0, 0}, b_lam = 0, b_isr = 0, b_base = 0, b_shape = 0;
@@ -155,7 +348,6 @@ __device__ __forceinline__ void tm_run(const int MU, const TmMaps& maps, const G
         bx_o[0] = tab->box[tid][0]; bx_o[1] = tab->box[tid][1]; bx_o[2] = tab->box[tid][2];
         b_lam = tab->box[tid][3]; b_isr = tab->box[tid][4]; b_base = tab->box[tid][5]; b_shape = tab->box[tid][6];
     }
-#endif
     uint64_t* const barS = bars;                 // [S_RING]
     uint64_t* const barR = bars + tm::S_RING;    // [R_RING]
     unsigned phases = 0;                         // bit s: parity of the next completion of barrier s (uniform over the CTA)
@@ -166,34 +358,8 @@ __device__ __forceinline__ void tm_run(const int MU, const TmMaps& maps, const G
 
     const long nitems = (long)pl.ntiles * pl.nseg;
     for (long item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int seg = (int)(item / pl.ntiles);
-        int tile = (int)(item % pl.ntiles);
-        const int x0 = (tile % pl.ntx) * tm::BX; tile /= pl.ntx;
-        const int y0 = (tile % pl.nty) * tm::BY;
-        const int z0 = (tile / pl.nty) * tm::BZ;
-        const int tb = pl.t_begin + seg * pl.seg_len;
-        const int len = min(pl.seg_len, pl.t_begin + pl.t_count - tb);
-
-#if GFB_TM_UNIFORM_ISSUE
-        // one part (all its boxes) of the slice in storage slot `tslot` into ring buffer `ring`: one elected thread of warp 0
-        // issues the copies back to back; every operand is warp-uniform (tile origin, box table from constant memory), so the
-        // compiler feeds the uniform-datapath UTMALDG without the per-lane ELECT / 8 x R2UR loop of a lane-per-box issue
-        auto copy_part = [&](int is_r, int tslot, int ring) {
-            if ((tid >> 5) != 0) return;
-            uint64_t* const bar = is_r ? barR + ring : barS + ring;
-            unsigned char* const part = is_r ? sR + ring * tm::R_BYTES : sS + ring * tm::S_BYTES;
-            if (elect_one()) {
-                mbar_arrive_expect_tx(bar, (unsigned)((is_r ? tm::R_MATS : tm::S_MATS) * tm::MAT_BYTES));
-                const int b0 = is_r ? tm::NBOX_S : 0, b1 = is_r ? tm::NBOX : tm::NBOX_S;
-#pragma unroll
-                for (int b = b0; b < b1; b++) {
-                    const int bcx = 2 * wrap(x0 + c_tm_box[b][0], g.nx), bcy = wrap(y0 + c_tm_box[b][1], g.ny), bcz = wrap(z0 + c_tm_box[b][2], g.nz);
-                    tma_load_4d(smem_u32(part + c_tm_box[b][5]), &maps.m[c_tm_box[b][6]], bcx, bcy, bcz, tslot * 36 + c_tm_box[b][3] * 9, bar);
-                }
-            }
-            __syncwarp();
-        };
-#else
+        const TmItem it = decode_item(pl, item);
+        const int x0 = it.x0, y0 = it.y0, z0 = it.z0, tb = it.tb, len = it.len;
         const int cx = 2 * wrap(x0 + bx_o[0], g.nx), cy = wrap(y0 + bx_o[1], g.ny), cz = wrap(z0 + bx_o[2], g.nz);
         // one part (all its boxes) of the slice in storage slot `tslot` into ring buffer `ring`; warp 0 only
         auto copy_part = [&](int is_r, int tslot, int ring) {
@@ -202,11 +368,10 @@ __device__ __forceinline__ void tm_run(const int MU, const TmMaps& maps, const G
             if (tid == 0) mbar_arrive_expect_tx(bar, (unsigned)((is_r ? tm::R_MATS : tm::S_MATS) * tm::MAT_BYTES));
             __syncwarp();
             if (is_producer && b_isr == is_r) {
-                unsigned char* const dst = (is_r ? sR + ring * tm::R_BYTES : sS + ring * tm::S_BYTES) + b_base;
+                unsigned char* const dst = (is_r ? sR + ring * tm::R_SLOT : sS + ring * tm::S_SLOT) + b_base;
                 tma_load_4d(smem_u32(dst), &maps.m[b_shape], cx, cy, cz, tslot * 36 + b_lam * 9, bar);
             }
         };
-#endif
         auto t_up = [&](int t) { return (t == g.tloc - 1) ? g.t_up_wrap : t + 1; };
 
         // ---- prologue: slice tb (full) and the S part of slice tb+1; the backward-t staple of slice tb from global memory
@@ -218,14 +383,7 @@ __device__ __forceinline__ void tm_run(const int MU, const TmMaps& maps, const G
         x.x = x0 + sx; x.y = y0 + sy; x.z = z0 + sz; x.t = tb;
         const unsigned s3 = (unsigned)s3_of(g, x);
         R2 G;
-        if (MU < 3) {
-            const Coord y = step(g, x, 3, -1);
-            const Coord ym = step(g, y, MU, +1);
-            const M3 A = load_link(uin, g, y, 3);
-            const M3 U = load_link(uin, g, y, MU);
-            const M3 C = load_link(uin, g, ym, 3);
-            G = r2_mul_nn(r2_mul_nn(rows01_dag(A), U), C);
-        }
+        if (MU < 3) G = first_backward_staple(MU, g, ar.uin, x);
         wait_bar(0);
         wait_bar(tm::S_RING + 0);
         wait_bar(1);
@@ -240,88 +398,12 @@ __device__ __forceinline__ void tm_run(const int MU, const TmMaps& maps, const G
                 copy_part(1, t + 1, (j + 1) & 1);
                 copy_part(0, t_up(t + 1), rs2);
             }
-
             // branch-free operand addressing (a ternary on the three ring bases compiled to divergent-branch regions that
             // ptxas could not schedule loads across): 32-bit shared address = Sc + offset + isR*(Rc-Sc) + isNext*(Sn-Sc)
-            const unsigned sc = smem_u32(sS + rs * tm::S_BYTES);
-            const unsigned d_r = smem_u32(sR + (j & 1) * tm::R_BYTES) - sc;
-            const unsigned d_n = smem_u32(sS + rs1 * tm::S_BYTES) - sc;
-            auto at = [&](int d) -> SmOp {
-                SmOp o;
-                o.p = sc + ((unsigned)d & 0xFFFFu) + (((unsigned)d >> 28) & 1u) * d_r + (((unsigned)d >> 29) & 1u) * d_n;
-                o.stride = (((unsigned)d >> 16) & 0xFFu) * 16u;
-                return o;
-            };
-
-            const unsigned zo = (unsigned)(t * 32 + MU * 8) * (unsigned)g.v3 + s3;
-            const unsigned zsb = (unsigned)g.v3 * 8u;
-            double z[8];
-            if (READ_Z) {
-#pragma unroll
-                for (int k = 0; k < 8; k++) z[k] = __ldg(reinterpret_cast<const double*>(reinterpret_cast<const char*>(zin + zo) + (size_t)k * zsb));
-            }
-
-            M3 V, U;
-            if (MU < 3) V = complete_su3(G);
-            else V = m3_zero();
-#if GFB_TM_DEBUG == 1
-#pragma unroll
-            for (int jj = 0; jj < 3; jj++) {
-                m3_add(V, lds_m3(at(od[1 + 6 * jj]))); m3_add(V, lds_m3(at(od[2 + 6 * jj]))); m3_add(V, lds_m3(at(od[3 + 6 * jj])));
-                if (jj < 2 || MU == 3) { m3_add(V, lds_m3(at(od[4 + 6 * jj]))); m3_add(V, lds_m3(at(od[5 + 6 * jj]))); m3_add(V, lds_m3(at(od[6 + 6 * jj]))); }
-            }
-            U = lds_m3(at(od[0]));
-#else
-            auto upper = [&](int jj) {  // A B C^dag
-                const R2 A = lds_rows01(at(od[1 + 6 * jj]));
-                const M3 B = lds_m3(at(od[2 + 6 * jj]));
-                const R2 T = r2_mul_nn(A, B);
-                const M3 C = lds_m3(at(od[3 + 6 * jj]));
-                acc_su3(V, r2_mul_nd(T, C));
-            };
-            auto lower = [&](int jj) {  // A^dag B C
-                const R2 A = lds_dag_rows01(at(od[4 + 6 * jj]));
-                const M3 B = lds_m3(at(od[5 + 6 * jj]));
-                const R2 T = r2_mul_nn(A, B);
-                const M3 C = lds_m3(at(od[6 + 6 * jj]));
-                acc_su3(V, r2_mul_nn(T, C));
-            };
-            upper(0); lower(0);
-            upper(1); lower(1);
-            if (MU == 3) {
-                upper(2); lower(2);
-                U = lds_m3(at(od[0]));
-            } else {
-                // nu = t: the upper staple U_t(x) U_mu(x+t) U_t(x+mu)^dag and the NEXT slice's backward staple
-                // U_t(x)^dag U_mu(x) U_t(x+mu) share A = U_t(x) and C = U_t(x+mu); B of the latter is the own link
-                const M3 A = lds_m3(at(od[13]));
-                const M3 C = lds_m3(at(od[15]));
-                {
-                    const M3 B = lds_m3(at(od[14]));
-                    const R2 T = r2_mul_nn(rows01(A), B);
-                    acc_su3(V, r2_mul_nd(T, C));
-                }
-                U = lds_m3(at(od[0]));
-                const R2 T = r2_mul_nn(rows01_dag(A), U);
-                G = r2_mul_nn(T, C);
-            }
-#endif
-
-            double f[8];
-            ta_coeffs_nd(U, V, f);
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                double v = a * f[k];
-                if (READ_Z) v = fma(b, z[k], v);
-                f[k] = v;
-                if (WRITE_Z) *reinterpret_cast<double*>(reinterpret_cast<char*>(zout + zo) + (size_t)k * zsb) = v;
-            }
-            if (DO_EXP) {
-                const M3 r = exp_ta_times_su3(f, c, U);
-                const unsigned uo = (unsigned)(t * 36 + MU * 9) * (unsigned)g.v3 + s3;
-                m3_store(uout + uo, (unsigned)g.v3, r);
-            }
-
+            const unsigned sc = smem_u32(sS + rs * tm::S_SLOT);
+            const unsigned d_r = smem_u32(sR + (j & 1) * tm::R_SLOT) - sc;
+            const unsigned d_n = smem_u32(sS + rs1 * tm::S_SLOT) - sc;
+            tm_step<READ_Z, WRITE_Z, DO_EXP>(MU, g, ar, od, t, s3, sc, d_r, d_n, G, [] {});
             // the next slice's parts (requested at the top of this step) must have landed; then every thread is done
             // reading this step's buffers and warp 0 may overwrite them
             if (more) {
@@ -334,24 +416,155 @@ __device__ __forceinline__ void tm_run(const int MU, const TmMaps& maps, const G
     }
 }
 
-constexpr size_t kTmBarOff = tm::SMEM_DATA;
-
 template <bool READ_Z, bool WRITE_Z, bool DO_EXP>
 __global__ void __launch_bounds__(tm::NTHREADS, 1)
-k_tmarch_fused(const __grid_constant__ TmMaps maps, const tm::Tables* __restrict__ tab, Geom g, TmPlan pl, const double2* __restrict__ uin, double2* __restrict__ uout,
-               const double* __restrict__ zin, double* __restrict__ zout, double a, double b, double c) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + kTmBarOff);
+k_tmarch_fused(const __grid_constant__ TmMaps maps, const tm::Tables* __restrict__ tab, Geom g, TmPlan pl, TmArgs ar) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + tm::BAR_OFF);
     if (threadIdx.x == 0) {
         for (int i = 0; i < tm::S_RING + tm::R_RING; i++) mbar_init(bars + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     const int mu = threadIdx.x / tm::SITES;  // warp-uniform: two warps per direction
-    tm_run<READ_Z, WRITE_Z, DO_EXP>(mu, maps, g, pl, uin, uout, zin, zout, a, b, c, smem, bars, tab);
+    tm_run<READ_Z, WRITE_Z, DO_EXP>(mu, maps, g, pl, ar, smem, bars, tab);
 }
 
-constexpr size_t kTmSmem = kTmBarOff + 8 * (tm::S_RING + tm::R_RING);
+// ---------------------------------------------------------------------------------------------------------------------
+// Variant B (default): warp-specialised.  Warps 0-7 are the 256 link-threads (consumers), warps 8-11 a producer warpgroup of
+// which one warp issues every tensor copy.  Registers move from the producer group to the consumers (setmaxnreg: 24 / 240 per
+// thread: 128*24 + 256*240 = the 64512 registers of a 384 x 168 launch).  No CTA-wide barrier in the march: every ring slot
+// has a FULL mbarrier (the copies' byte count) and an EMPTY mbarrier (one arrival per consumer warp, given as soon as the
+// warp has consumed the slot's operands, i.e. BEFORE its exponential), so the eight consumer warps drift apart by up to a
+// slice instead of meeting once per step behind the warp that also had to issue 21 copies (variant A: 8 % barrier stall,
+// 2100 of a step's 11250 cycles spent by warp 0 on UTMALDG issue -- profiles/r1_tmarch.md).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kWsThreads = tm::NTHREADS + 128;
+constexpr int kNBars = tm::S_RING + tm::R_RING;  // FULL barriers [0, kNBars), EMPTY barriers [kNBars, 2 kNBars)
+
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(N)); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+
+__device__ __noinline__ void tm_producer(const TmMaps& maps, const Geom& g, const TmPlan& pl, unsigned char* smem, uint64_t* bars) {
+    unsigned char* const sS = smem;
+    unsigned char* const sR = smem + tm::S_RING * tm::S_SLOT;
+    unsigned ephase = ~0u;  // EMPTY barriers start "released": the first wait on each passes (parity of the preceding phase)
+    const bool leader = elect_one();
+    const long nitems = (long)pl.ntiles * pl.nseg;
+    for (long item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const TmItem it = decode_item(pl, item);
+        // every box of one part of the slice in storage slot `tslot` into ring slot `ring`, once the consumers released it
+        auto fill = [&](int is_r, int tslot, int ring) {
+            const int s = is_r ? tm::S_RING + ring : ring;
+            mbar_wait(bars + kNBars + s, (ephase >> s) & 1u);
+            ephase ^= 1u << s;
+            if (leader) {
+                uint64_t* const bar = bars + s;
+                unsigned char* const part = is_r ? sR + ring * tm::R_SLOT : sS + ring * tm::S_SLOT;
+                mbar_arrive_expect_tx(bar, (unsigned)((is_r ? tm::R_MATS : tm::S_MATS) * tm::MAT_BYTES));
+                const int b0 = is_r ? tm::NBOX_S : 0, b1 = is_r ? tm::NBOX : tm::NBOX_S;
+                for (int b = b0; b < b1; b++) {
+                    const int bcx = 2 * wrap(it.x0 + c_tm_box[b][0], g.nx), bcy = wrap(it.y0 + c_tm_box[b][1], g.ny), bcz = wrap(it.z0 + c_tm_box[b][2], g.nz);
+                    tma_load_4d(smem_u32(part + c_tm_box[b][5]), &maps.m[c_tm_box[b][6]], bcx, bcy, bcz, tslot * 36 + c_tm_box[b][3] * 9, bar);
+                }
+            }
+            __syncwarp();
+        };
+        auto t_up = [&](int t) { return (t == g.tloc - 1) ? g.t_up_wrap : t + 1; };
+        fill(0, it.tb, 0);
+        fill(1, it.tb, 0);
+        fill(0, t_up(it.tb), 1);
+        int rs = 0;
+        for (int j = 0; j + 1 < it.len; j++) {
+            const int t = it.tb + j;
+            const int rs1 = (rs == 2) ? 0 : rs + 1, rs2 = (rs1 == 2) ? 0 : rs1 + 1;
+            fill(1, t + 1, (j + 1) & 1);
+            fill(0, t_up(t + 1), rs2);
+            rs = rs1;
+        }
+    }
+}
+
+template <bool READ_Z, bool WRITE_Z, bool DO_EXP>
+__device__ __forceinline__ void tm_consumer(const int MU, const Geom& g, const TmPlan& pl, const TmArgs& ar, unsigned char* smem, uint64_t* bars,
+                                            const tm::Tables* __restrict__ tab) {
+    const int tid = threadIdx.x;
+    const int sidx = tid & (tm::SITES - 1);
+    const int sx = sidx & (tm::BX - 1), sy = (sidx / tm::BX) & (tm::BY - 1), sz = sidx / (tm::BX * tm::BY);
+    unsigned char* const sS = smem;
+    unsigned char* const sR = smem + tm::S_RING * tm::S_SLOT;
+    int od[tm::NDESC];
+#pragma unroll
+    for (int i = 0; i < tm::NDESC; i++) od[i] = tab->desc[i][tid];
+    unsigned fphase = 0;  // bit s: parity of the next completion of FULL barrier s
+    auto wait_full = [&](int s) {
+        mbar_wait(bars + s, (fphase >> s) & 1u);
+        fphase ^= 1u << s;
+    };
+    const bool lane0 = (tid & 31) == 0;
+    const long nitems = (long)pl.ntiles * pl.nseg;
+    for (long item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const TmItem it = decode_item(pl, item);
+        Coord x;
+        x.x = it.x0 + sx; x.y = it.y0 + sy; x.z = it.z0 + sz; x.t = it.tb;
+        const unsigned s3 = (unsigned)s3_of(g, x);
+        R2 G;
+        if (MU < 3) G = first_backward_staple(MU, g, ar.uin, x);
+        wait_full(0);               // S part of slice tb
+        wait_full(tm::S_RING + 0);  // R part of slice tb
+        wait_full(1);               // S part of slice tb+1
+        int rs = 0;
+        for (int j = 0; j < it.len; j++) {
+            const int t = it.tb + j;
+            const int rs1 = (rs == 2) ? 0 : rs + 1;
+            if (j > 0) {  // filled while the previous step ran
+                wait_full(tm::S_RING + (j & 1));
+                wait_full(rs1);
+            }
+            const unsigned sc = smem_u32(sS + rs * tm::S_SLOT);
+            const unsigned d_r = smem_u32(sR + (j & 1) * tm::R_SLOT) - sc;
+            const unsigned d_n = smem_u32(sS + rs1 * tm::S_SLOT) - sc;
+            const bool last = j + 1 == it.len;
+            tm_step<READ_Z, WRITE_Z, DO_EXP>(MU, g, ar, od, t, s3, sc, d_r, d_n, G, [&] {
+                // this warp is done with slice t's S and R parts (the S part of slice t+1 stays for the next step, unless this
+                // was the last step of the segment)
+                __syncwarp();
+                if (lane0) {
+                    mbar_arrive(bars + kNBars + rs);
+                    mbar_arrive(bars + kNBars + tm::S_RING + (j & 1));
+                    if (last) mbar_arrive(bars + kNBars + rs1);
+                }
+            });
+            rs = rs1;
+        }
+    }
+}
+
+template <bool READ_Z, bool WRITE_Z, bool DO_EXP>
+__global__ void __launch_bounds__(kWsThreads, 1)
+k_tmarch_ws(const __grid_constant__ TmMaps maps, const tm::Tables* __restrict__ tab, Geom g, TmPlan pl, TmArgs ar) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + tm::BAR_OFF);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kNBars; i++) mbar_init(bars + i, 1);
+        for (int i = 0; i < kNBars; i++) mbar_init(bars + kNBars + i, tm::NTHREADS / 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x >= tm::NTHREADS) {
+        reg_dec<GFB_TM_PREGS>();
+        if (threadIdx.x < tm::NTHREADS + 32) tm_producer(maps, g, pl, smem, bars);
+        return;
+    }
+    reg_inc<((64512 - 128 * GFB_TM_PREGS) / 256) & ~7>();
+    const int mu = threadIdx.x / tm::SITES;  // warp-uniform: two warps per direction
+    tm_consumer<READ_Z, WRITE_Z, DO_EXP>(mu, g, pl, ar, smem, bars, tab);
+}
+
+constexpr size_t kTmSmem = tm::SMEM_DATA;  // 232448 = the opt-in maximum; the mbarriers live in the tail of R slot 0
 
 // t-segments: enough (segment, tile) items to fill the SMs evenly, as few segment prologues as possible
 TmPlan make_plan(const Geom& g, int t_begin, int t_count, int nsm) {
@@ -396,28 +609,29 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // tensor maps of a link buffer viewed as [nslots*36 planes][nz][ny][2*nx doubles], one per box shape; cached per buffer
-const TmMaps* tensor_maps_for(const double2* u, const Geom& g) {
+// Returned BY VALUE (copied under the lock): the cache may be cleared by another thread's call.
+bool tensor_maps_for(const double2* u, const Geom& g, bool swizzle, TmMaps* out) {
     struct Key {
         const void* p;
-        int nx, ny, nz, nslots;
-        bool operator==(const Key& o) const { return p == o.p && nx == o.nx && ny == o.ny && nz == o.nz && nslots == o.nslots; }
+        int nx, ny, nz, nslots, swz;
+        bool operator==(const Key& o) const { return p == o.p && nx == o.nx && ny == o.ny && nz == o.nz && nslots == o.nslots && swz == o.swz; }
     };
     struct Hash {
         size_t operator()(const Key& k) const {
-            return std::hash<const void*>()(k.p) ^ ((size_t)k.nx * 1315423911u) ^ ((size_t)k.ny << 12) ^ ((size_t)k.nz << 24) ^ ((size_t)k.nslots << 36);
+            return std::hash<const void*>()(k.p) ^ ((size_t)k.nx * 1315423911u) ^ ((size_t)k.ny << 12) ^ ((size_t)k.nz << 24) ^ ((size_t)k.nslots << 36) ^ (size_t)k.swz;
         }
     };
     static std::unordered_map<Key, TmMaps, Hash> cache;
     static std::mutex mtx;
     static EncodeTiledFn encode = nullptr;
     std::lock_guard<std::mutex> lock(mtx);
-    const Key key{u, g.nx, g.ny, g.nz, g.nslots};
+    const Key key{u, g.nx, g.ny, g.nz, g.nslots, swizzle ? 1 : 0};
     auto it = cache.find(key);
-    if (it != cache.end()) return &it->second;
+    if (it != cache.end()) { *out = it->second; return true; }
     if (!encode) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return false;
         encode = reinterpret_cast<EncodeTiledFn>(fn);
     }
     TmMaps maps;
@@ -428,67 +642,83 @@ const TmMaps* tensor_maps_for(const double2* u, const Geom& g) {
         int e[3];
         tm::shape_extent(s / 3, e);
         const cuuint32_t box[4] = {(cuuint32_t)e[0] * 2, (cuuint32_t)e[1], (cuuint32_t)e[2], (cuuint32_t)(9 * (s % 3 + 1))};
+        // full-tile boxes (shape 0: rows of 8 x-sites = 128 bytes) are stored with the 128-byte swizzle (tmarch_geom.h, lookup())
+        const CUtensorMapSwizzle sw = (swizzle && s / 3 == 0) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE;
         if (encode(&maps.m[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double2*>(u), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            return nullptr;
+                   sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
     }
     if (cache.size() > 1024) cache.clear();  // buffers come and go with the fields; the maps are cheap to rebuild
-    return &cache.emplace(key, maps).first->second;
+    cache.emplace(key, maps);
+    *out = maps;
+    return true;
 }
 
 }  // namespace
 
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 // Returns false when the launch is not covered (tile does not divide the lattice, strided slice set, in-place links):
-// the caller then uses k_force_fused.  GFB200_TMARCH=0 disables the kernel.
+// the caller then uses k_force_fused.  Environment (read per launch so that tests can compare variants in one process):
+//   GFB200_TMARCH=0 disables the kernel;  GFB200_TMARCH_WS=0 selects variant A (no producer warpgroup);
+//   GFB200_TMARCH_SWIZZLE=0 copies the tile boxes linearly;  GFB200_TMARCH_SEGLEN=n forces the t-segment length.
 bool launch_tmarch_fused(cudaStream_t st, const Geom& g, int t_begin, int t_count, const double2* uin, double2* uout, const double* zin, double* zout,
                          const FusedArgs& fa) {
-    const char* em = getenv("GFB200_TMARCH");  // read per launch so that tests can compare both kernels in one process
-    const int mode = em ? atoi(em) : 1;
-    if (!mode) return false;
-    if (g.t_stride != 1 || t_count < 2) return false;
-    // Short slab interiors stay in k_force_fused: with 8 slices per GPU (6 interior) the step is set by the exchange chain, a
-    // segment start is 10 % of a 6-slice march, and all-k_force_fused measured 3-6 % faster on 8 GPUs (profiles/r1_tmarch.md);
-    // from 16 slices per GPU on the t-marching interior wins (2.98 vs ~3.6 ms at 64^4 on 4 GPUs).  GFB200_TMARCH=2 forces it.
-    if (g.nslots > g.tloc && t_count < 8 && mode != 2) return false;
+    if (!env_int("GFB200_TMARCH", 1)) return false;
+    if (g.t_stride != 1 || t_count < 1) return false;
     if (g.nx % tm::BX || g.ny % tm::BY || g.nz % tm::BZ) return false;
     if (uout == uin) return false;
     int dev = 0;
     cudaGetDevice(&dev);
     static int nsm = 0;
     if (nsm == 0) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    // Multi-GPU slabs: a persistent grid fills every SM for the whole pass (231 KB of shared memory, 255 registers per thread), so
-    // NCCL's send/recv kernels of the overlapped halo exchange could not start before it ends (measured: 7.5 ms instead of 5.2 ms
-    // per 64^4/2 step).  There the grid is one CTA per (tile, segment) item instead: SMs free up every item and the high-priority
-    // halo stream gets them first.  GFB200_TMARCH_RESERVE_SMS=n additionally keeps n SMs out of the plan.
-    const bool slab = g.nslots > g.tloc;
-    int reserve = 0;
-    if (const char* er = getenv("GFB200_TMARCH_RESERVE_SMS")) reserve = atoi(er);
-    if (reserve < 0 || reserve >= nsm) reserve = 0;
-    int persistent = slab ? 0 : 1;
-    if (const char* ep = getenv("GFB200_TMARCH_PERSISTENT")) persistent = atoi(ep);
-    const int nsm_use = nsm - reserve;
-    TmPlan pl = make_plan(g, t_begin, t_count, nsm_use);
-    if (const char* e = getenv("GFB200_TMARCH_SEGLEN")) {  // test hook: force the t-segment length
-        const int len = atoi(e);
+    const bool ws = env_int("GFB200_TMARCH_WS", 1) != 0;
+    const bool swizzle = env_int("GFB200_TMARCH_SWIZZLE", 1) != 0;
+    TmPlan pl = make_plan(g, t_begin, t_count, nsm);
+    {
+        const int len = env_int("GFB200_TMARCH_SEGLEN", 0);  // test hook
         if (len >= 1) { pl.seg_len = len < t_count ? len : t_count; pl.nseg = (t_count + pl.seg_len - 1) / pl.seg_len; }
     }
-    const TmMaps* maps = tensor_maps_for(uin, g);
+    TmMaps maps;
     const tm::Tables* tab = device_tables(dev);
-    if (!maps || !tab) return false;
+    if (!tab || !tensor_maps_for(uin, g, swizzle, &maps)) return false;
+    TmArgs ar;
+    ar.uin = uin; ar.uout = uout; ar.zin = zin; ar.zout = zout;
+    ar.a = fa.a; ar.b = fa.b; ar.c = fa.c;
+    ar.swz = swizzle ? 0x70u : 0u;
+    ar.peer_prev = fa.do_exp ? fa.peer_prev : nullptr;
+    ar.peer_next = fa.do_exp ? fa.peer_next : nullptr;
     const long nitems = (long)pl.ntiles * pl.nseg;
-    const unsigned grid = (unsigned)((!persistent || nitems < nsm_use) ? nitems : nsm_use);
+    // persistent: one CTA per SM (232448 bytes of shared memory each).  NCCL-overlapped slab interiors (fa.leave_sms) launch one
+    // CTA per item instead, so that SMs free up for the send/recv kernels of the halo stream (profiles/r1_tmarch.md)
+    const unsigned grid = (unsigned)((nitems < nsm || fa.leave_sms) ? nitems : nsm);
 #define GFB_LAUNCH_TM(R, W, E)                                                                                                  \
     do {                                                                                                                        \
-        auto kern = k_tmarch_fused<R, W, E>;                                                                                    \
-        static bool attr_set[64] = {};  /* per device: one process may drive several GPUs */                                    \
-        if (!attr_set[dev & 63]) {                                                                                              \
-            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmSmem) != cudaSuccess) {         \
-                cudaGetLastError();                                                                                             \
-                return false;                                                                                                   \
+        static bool attr_set[2][64] = {};  /* per device: one process may drive several GPUs */                                 \
+        if (ws) {                                                                                                               \
+            auto kern = k_tmarch_ws<R, W, E>;                                                                                   \
+            if (!attr_set[1][dev & 63]) {                                                                                       \
+                if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmSmem) != cudaSuccess) {     \
+                    cudaGetLastError();                                                                                         \
+                    return false;                                                                                               \
+                }                                                                                                               \
+                attr_set[1][dev & 63] = true;                                                                                   \
             }                                                                                                                   \
-            attr_set[dev & 63] = true;                                                                                          \
+            kern<<<grid, kWsThreads, kTmSmem, st>>>(maps, tab, g, pl, ar);                                                      \
+        } else {                                                                                                                \
+            auto kern = k_tmarch_fused<R, W, E>;                                                                                \
+            if (!attr_set[0][dev & 63]) {                                                                                       \
+                if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmSmem) != cudaSuccess) {     \
+                    cudaGetLastError();                                                                                         \
+                    return false;                                                                                               \
+                }                                                                                                               \
+                attr_set[0][dev & 63] = true;                                                                                   \
+            }                                                                                                                   \
+            kern<<<grid, tm::NTHREADS, kTmSmem, st>>>(maps, tab, g, pl, ar);                                                    \
         }                                                                                                                       \
-        kern<<<grid, tm::NTHREADS, kTmSmem, st>>>(*maps, tab, g, pl, uin, uout, zin, zout, fa.a, fa.b, fa.c);                                \
     } while (0)
     if (fa.read_z) {
         if (fa.do_exp) GFB_LAUNCH_TM(true, true, true);

@@ -43,7 +43,13 @@ constexpr int S_MATS = 248, R_MATS = 428;
 constexpr int S_BYTES = 35712;           // 248 matrices, every S box is a multiple of 8 matrices (no padding)
 constexpr int R_BYTES = 61952;           // 428 matrices + 320 bytes of padding (box bases are 128-byte aligned for TMA)
 constexpr int S_RING = 3, R_RING = 2;
-constexpr int SMEM_DATA = S_RING * S_BYTES + R_RING * R_BYTES;  // 231040
+// Ring strides are multiples of 1024 bytes: the tile boxes (8 x-sites = one 128-byte row per (k, z, y)) are copied with the
+// 128-byte TMA swizzle, whose XOR pattern is a function of the ABSOLUTE shared-memory address bits 7-9; with every tile box at
+// a 1024-byte multiple the pattern is the same in every ring slot (see lookup(): swizzled operands).  The tail of R slot 0
+// (R_SLOT - R_BYTES = 512 bytes) holds the mbarriers, so the whole 227 KB opt-in maximum is used: 3*35840 + 2*62464 = 232448.
+constexpr int S_SLOT = 35840, R_SLOT = 62464;
+constexpr int SMEM_DATA = S_RING * S_SLOT + R_RING * R_SLOT;  // 232448
+constexpr int BAR_OFF = S_RING * S_SLOT + R_BYTES;             // mbarriers: up to 64 of them in the tail of R slot 0
 
 // One TMA copy: the links of nlam consecutive directions lam .. lam+nlam-1 on a box of positions (their 9*nlam element planes
 // are contiguous in a slice, so directions that need the same positions share a copy: 21 copies per slice instead of 31).
@@ -126,7 +132,14 @@ TM_HD int make_boxes(Box* b) {
 
 // operand descriptor of link lam at tile-relative position (x, y, z):
 //   bits 0-15 byte offset of element 0 inside its part, bits 16-23 box volume n (element k is k*n*16 bytes further),
-//   bit 24 set when the box belongs to the R part;  -1 when the position is not resident
+//   bit 24 set when the box belongs to the R part, bit 25 when the box is a full tile (copied with the 128-byte swizzle: the
+//   16-byte chunk index, address bits 4-6, is XORed with address bits 7-9; n*16 = 1024 there, so the XOR term is the same for
+//   all nine elements);  -1 when the position is not resident.
+// Why the swizzle: a warp reads 8 x-consecutive sites per LDS.128 phase.  Unshifted that is one 128-byte row.  Shifted by +x
+// it is positions 1..7 of the row plus one element of the +x face box, which in the linear layout lands on the banks of one
+// of the seven (2 wavefronts instead of 1; 19 % of all wavefronts were such conflicts, profiles/r1_tmarch.md).  With the XOR
+// swizzle, row r = y + 4z (+ 8k) holds position p at chunk p ^ (r & 7), so positions 1..7 leave exactly chunk r & 7 free --
+// and the face box [k][z][y] (dense, 128-byte aligned) holds element (y, z) at chunk (y + 4z) & 7 = r & 7: conflict-free.
 TM_HD int lookup(const Box* b, int lam, int x, int y, int z) {
     for (int i = 0; i < NBOX; i++) {
         if (lam < b[i].lam || lam >= b[i].lam + b[i].nlam) continue;
@@ -134,7 +147,8 @@ TM_HD int lookup(const Box* b, int lam, int x, int y, int z) {
         if (dx < 0 || dy < 0 || dz < 0 || dx >= b[i].e[0] || dy >= b[i].e[1] || dz >= b[i].e[2]) continue;
         const int idx = dx + b[i].e[0] * (dy + b[i].e[1] * dz);
         const int n = box_volume(b[i]);
-        return (b[i].base + (lam - b[i].lam) * 9 * n * 16 + idx * 16) | (n << 16) | ((b[i].is_r ? 1 : 0) << 24);
+        const int swz = (b[i].e[0] == BX && b[i].e[1] == BY && b[i].e[2] == BZ) ? 1 : 0;
+        return (b[i].base + (lam - b[i].lam) * 9 * n * 16 + idx * 16) | (n << 16) | ((b[i].is_r ? 1 : 0) << 24) | (swz << 25);
     }
     return -1;
 }
@@ -180,12 +194,15 @@ TM_HD void make_operands(const Box* b, int sx, int sy, int sz, int mu, Operands*
 
 // Final per-thread operand descriptors of the kernel, in the order the hot loop uses them:
 //   d[0] own link;  d[1+6j .. 6+6j] = up A,B,C, dn A,B,C of iteration j (dn of the nu = t iteration of a spatial link: unused, 0)
-//   bits 0-15 byte offset, 16-23 box volume, bit 28: R part of slice t, bit 29: S part of slice t+1 (neither: S part of slice t)
+//   bits 0-15 byte offset, 16-23 box volume, bit 28: R part of slice t, bit 29: S part of slice t+1 (neither: S part of slice t),
+//   bit 30: the box is swizzled (full tile)
 constexpr int NDESC = 19;
 TM_HD void make_descriptors(const Box* b, int sx, int sy, int sz, int mu, int* d) {
     Operands op;
     make_operands(b, sx, sy, sz, mu, &op);
-    d[0] = (op.own & 0xFFFFFF) | (((op.own >> 24) & 1) << 28);
+    // lookup() bits 24 (R part) and 25 (swizzled) move to bits 28 and 30
+    auto fin = [](int v, bool next) { return (v & 0xFFFFFF) | (next ? (2 << 28) : (((v >> 24) & 1) << 28)) | (((v >> 25) & 1) << 30); };
+    d[0] = fin(op.own, false);
     for (int j = 0; j < 3; j++) {
         const int nu = staple_dir(mu, j);
         for (int o = 0; o < 3; o++) {
@@ -193,8 +210,8 @@ TM_HD void make_descriptors(const Box* b, int sx, int sy, int sz, int mu, int* d
             const bool next_up = (o == 1 && mu < 3 && nu == 3) || (o == 2 && mu == 3);
             const bool next_dn = (o == 2 && mu == 3);
             const int u = op.up[j][o], l = op.dn[j][o];
-            d[1 + 6 * j + o] = next_up ? ((u & 0xFFFFFF) | (2 << 28)) : ((u & 0xFFFFFF) | (((u >> 24) & 1) << 28));
-            d[4 + 6 * j + o] = (nu == 3) ? 0 : (next_dn ? ((l & 0xFFFFFF) | (2 << 28)) : ((l & 0xFFFFFF) | (((l >> 24) & 1) << 28)));
+            d[1 + 6 * j + o] = fin(u, next_up);
+            d[4 + 6 * j + o] = (nu == 3) ? 0 : fin(l, next_dn);
         }
     }
 }

@@ -45,9 +45,16 @@ int main(int argc, char** argv) {
         if (s != S_BYTES || r != R_BYTES || sm != S_MATS || rm != R_MATS) { printf("part sizes %d %d %d %d\n", s, r, sm, rm); return 1; }
         if (R_BYTES >= 65536) { printf("descriptor offset overflow\n"); return 1; }
     }
-    // shared memory as 16-byte elements holding (link id * 9 + k)
-    std::vector<long> S(S_RING * S_BYTES / 16, -1), R(R_RING * R_BYTES / 16, -1);
-    long checked = 0;
+    // ring strides: multiples of 1024 bytes (the swizzle pattern must be the same in every slot), mbarriers in the tail of R slot 0
+    if (S_SLOT % 1024 || R_SLOT % 1024 || S_SLOT < S_BYTES || R_SLOT < R_BYTES + 8 * 16 || SMEM_DATA != S_RING * S_SLOT + R_RING * R_SLOT ||
+        SMEM_DATA > 232448 || BAR_OFF < S_RING * S_SLOT + R_BYTES || BAR_OFF + 8 * 16 > S_RING * S_SLOT + R_SLOT) { printf("ring layout\n"); return 1; }
+    // shared memory (absolute byte address / 16) as 16-byte elements holding (link id * 9 + k); tile boxes are written the way
+    // the 128-byte TMA swizzle writes them: chunk index (address bits 4-6) XOR address bits 7-9
+    const bool swizzle = argc > 6 ? atoi(argv[6]) != 0 : true;
+    std::vector<long> M(SMEM_DATA / 16, -1);
+    auto part_base = [&](int is_r, int ring) { return is_r ? S_RING * S_SLOT + ring * R_SLOT : ring * S_SLOT; };
+    auto swz = [&](unsigned a) { return swizzle ? a ^ (((a >> 7) & 7u) << 4) : a; };
+    long checked = 0, wavefronts = 0, ideal = 0, shifted_px_conflicts = 0;
     const int nseg = (NTg + seg_len - 1) / seg_len;
     for (int z0 = 0; z0 < NZg; z0 += BZ) for (int y0 = 0; y0 < NYg; y0 += BY) for (int x0 = 0; x0 < NXg; x0 += BX)
     for (int seg = 0; seg < nseg; seg++) {
@@ -60,10 +67,14 @@ int main(int argc, char** argv) {
                 if (b.is_r != is_r) continue;
                 const int ox = wrapc(x0 + b.o[0], NXg), oy = wrapc(y0 + b.o[1], NYg), oz = wrapc(z0 + b.o[2], NZg);
                 if (ox + b.e[0] > NXg || oy + b.e[1] > NYg || oz + b.e[2] > NZg) { printf("box crosses the boundary\n"); exit(1); }
-                long* dst = (is_r ? R.data() + (size_t)ring * R_BYTES / 16 : S.data() + (size_t)ring * S_BYTES / 16) + b.base / 16;
+                const bool tile = b.e[0] == BX && b.e[1] == BY && b.e[2] == BZ;
+                unsigned dst = (unsigned)(part_base(is_r, ring) + b.base);
+                if (tile && (dst & 1023)) { printf("swizzled box not 1024-aligned\n"); exit(1); }
                 // destination = the copy's own order: [plane = (direction - lam)*9 + k][z][y][x]
-                for (int pl = 0; pl < 9 * b.nlam; pl++) for (int z = 0; z < b.e[2]; z++) for (int y = 0; y < b.e[1]; y++) for (int x = 0; x < b.e[0]; x++)
-                    *dst++ = link_id(b.lam + pl / 9, ox + x, oy + y, oz + z, t) * 9 + pl % 9;
+                for (int pl = 0; pl < 9 * b.nlam; pl++) for (int z = 0; z < b.e[2]; z++) for (int y = 0; y < b.e[1]; y++) for (int x = 0; x < b.e[0]; x++) {
+                    M[(tile ? swz(dst) : dst) / 16] = link_id(b.lam + pl / 9, ox + x, oy + y, oz + z, t) * 9 + pl % 9;
+                    dst += 16;
+                }
             }
         };
         copy_part(0, tb, 0); copy_part(1, tb, 0); copy_part(0, tb + 1, 1);
@@ -71,24 +82,47 @@ int main(int argc, char** argv) {
         for (int j = 0; j < len; j++) {
             const int t = tb + j;
             const int rs1 = (rs + 1) % 3, rs2 = (rs1 + 1) % 3;
+            // the kernel's address arithmetic (tm_step, `at`): base of the S slot of slice t + offset + R / next-S displacement,
+            // XOR for swizzled boxes; element k is k*n*16 bytes further
+            const unsigned sc = (unsigned)part_base(0, rs), d_r = (unsigned)part_base(1, j & 1) - sc, d_n = (unsigned)part_base(0, rs1) - sc;
+            auto addr = [&](int d) {
+                unsigned p = sc + ((unsigned)d & 0xFFFFu) + (((unsigned)d >> 28) & 1u) * d_r + (((unsigned)d >> 29) & 1u) * d_n;
+                p ^= (p >> 3) & ((((unsigned)d >> 30) & 1u) * (swizzle ? 0x70u : 0u));
+                return p;
+            };
             // emulate the asynchronous prefetch landing at the END of the step: read first, copy afterwards
             // an operand is read as 9 elements at stride n*16 bytes; all nine must be the same link, k = 0..8 in order
-            auto fetch = [&](const std::vector<long>& part, size_t part_base16, int d) {
-                const int off = d & 0xFFFF, n = (d >> 16) & 0xFF;
+            auto rd = [&](int d) {
+                const unsigned p = addr(d), n = ((unsigned)d >> 16) & 0xFFu;
                 long id = -1;
                 for (int k = 0; k < 9; k++) {
-                    const long v = part[part_base16 + (off + k * n * 16) / 16];
+                    const long v = M[(p + k * n * 16) / 16];
                     if (v < 0 || v % 9 != k || (k > 0 && v / 9 != id)) { printf("bad element k=%d\n", k); exit(1); }
                     id = v / 9;
                 }
                 return id;
             };
-            // final descriptors (tm::make_descriptors): bit 28 = R part of slice t, bit 29 = S part of slice t+1
-            auto rd = [&](int d) {
-                if ((d >> 29) & 1) return fetch(S, (size_t)rs1 * S_BYTES / 16, d);
-                if ((d >> 28) & 1) return fetch(R, (size_t)(j & 1) * R_BYTES / 16, d);
-                return fetch(S, (size_t)rs * S_BYTES / 16, d);
+            // bank conflicts of one LDS.128 phase: the 8 x-consecutive lanes of a (mu, sz, sy) row read element 0 of descriptor i
+            auto phase_wavefronts = [&](int mu, int sz, int sy, int i) {
+                int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, worst = 0;
+                for (int sx = 0; sx < BX; sx++) {
+                    int d[NDESC];
+                    make_descriptors(boxes, sx, sy, sz, mu, d);
+                    if (d[i] == 0 && i != 0) return 0;  // unused slot (nu = t lower staple of a spatial link)
+                    const int c = (addr(d[i]) >> 4) & 7;
+                    if (++cnt[c] > worst) worst = cnt[c];
+                }
+                return worst;
             };
+            if (z0 == 0 && y0 == 0 && x0 == 0 && seg == 0)
+                for (int mu = 0; mu < 4; mu++) for (int sz = 0; sz < BZ; sz++) for (int sy = 0; sy < BY; sy++) for (int i = 0; i < NDESC; i++) {
+                    const int w = phase_wavefronts(mu, sz, sy, i);
+                    if (!w) continue;
+                    wavefronts += w; ideal += 1;
+                    // the reads the swizzle is for: +x shifted operands of interior rows (tile box + the +x face box)
+                    const bool px = (i == 2 && staple_dir(mu, 0) == 0) || (mu == 0 && (i == 3 || i == 9 || i == 15));
+                    if (swizzle && px && w != 1) shifted_px_conflicts++;
+                }
             for (int mu = 0; mu < 4; mu++) for (int sz = 0; sz < BZ; sz++) for (int sy = 0; sy < BY; sy++) for (int sx = 0; sx < BX; sx++) {
                 int d[NDESC];
                 make_descriptors(boxes, sx, sy, sz, mu, d);
@@ -119,6 +153,7 @@ int main(int argc, char** argv) {
             rs = rs1;
         }
     }
-    printf("ok %ld operand reads\n", checked);
+    if (shifted_px_conflicts) { printf("+x shifted reads of tile boxes still conflict: %ld\n", shifted_px_conflicts); return 1; }
+    printf("ok %ld operand reads, LDS wavefronts per phase %.3f (%s)\n", checked, ideal ? (double)wavefronts / ideal : 0.0, swizzle ? "swizzled" : "linear");
     return 0;
 }
