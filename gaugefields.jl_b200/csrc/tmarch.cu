@@ -21,6 +21,7 @@
 #include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
 
 #include <cstdint>
+#include <cmath>
 #include <cstdlib>
 #include <mutex>
 #include <unordered_map>
@@ -47,6 +48,11 @@ struct TmPlan {
     int t_begin, t_count;  // local slices covered by the launch (contiguous)
     int seg_len, nseg;     // t-segments: item = (segment, tile)
     int ntx, nty, ntz, ntiles;
+    // L2 blocking of the tile order: tiles are enumerated x fastest inside blocks of ntx x by x bz tiles (about one block = the
+    // tiles the SMs march through concurrently), blocks y fastest.  The halo links of a tile then belong to tiles that march
+    // at the same time (L2 hits); with the plain x,y,z order a wave of 148 tiles at 64^3 is one z-layer of tiles whose z-halos
+    // were loaded a whole wave (hundreds of MB) earlier: 2783 B/site of DRAM traffic instead of 1664 (profiles/r2_tmarch.md)
+    int by, bz;
 };
 
 
@@ -160,10 +166,10 @@ struct TmItem {
 __device__ __forceinline__ TmItem decode_item(const TmPlan& pl, long item) {
     TmItem it;
     const int seg = (int)(item / pl.ntiles);
-    int tile = (int)(item % pl.ntiles);
-    it.x0 = (tile % pl.ntx) * tm::BX; tile /= pl.ntx;
-    it.y0 = (tile % pl.nty) * tm::BY;
-    it.z0 = (tile / pl.nty) * tm::BZ;
+    const int r = (int)(item % pl.ntiles);
+    int tx, ty, tz;
+    tm::tile_of(pl.ntx, pl.nty, pl.ntz, pl.by, pl.bz, r, &tx, &ty, &tz);
+    it.x0 = tx * tm::BX; it.y0 = ty * tm::BY; it.z0 = tz * tm::BZ;
     it.tb = pl.t_begin + seg * pl.seg_len;
     it.len = min(pl.seg_len, pl.t_begin + pl.t_count - it.tb);
     return it;
@@ -585,6 +591,13 @@ TmPlan make_plan(const Geom& g, int t_begin, int t_count, int nsm) {
     }
     pl.seg_len = (t_count + best_nseg - 1) / best_nseg;
     pl.nseg = (t_count + pl.seg_len - 1) / pl.seg_len;
+    // block of concurrently marched tiles: ntx x by x bz ~ nsm tiles, about square in sites (BY*by ~ BZ*bz)
+    const double per_x = (double)nsm / pl.ntx;
+    int by = (int)(std::sqrt(per_x * tm::BZ / tm::BY) + 0.5);
+    by = by < 1 ? 1 : (by > pl.nty ? pl.nty : by);
+    int bz = (int)(per_x / by + 0.5);
+    bz = bz < 1 ? 1 : (bz > pl.ntz ? pl.ntz : bz);
+    pl.by = by; pl.bz = bz;
     return pl;
 }
 
@@ -682,6 +695,15 @@ bool launch_tmarch_fused(cudaStream_t st, const Geom& g, int t_begin, int t_coun
         const int len = env_int("GFB200_TMARCH_SEGLEN", 0);  // test hook
         if (len >= 1) { pl.seg_len = len < t_count ? len : t_count; pl.nseg = (t_count + pl.seg_len - 1) / pl.seg_len; }
     }
+    {
+        const int by = env_int("GFB200_TMARCH_BY", 0), bz = env_int("GFB200_TMARCH_BZ", 0);  // tuning hooks: tile-block shape
+        if (by >= 1) pl.by = by < pl.nty ? by : pl.nty;
+        if (bz >= 1) pl.bz = bz < pl.ntz ? bz : pl.ntz;
+    }
+    const long nitems = (long)pl.ntiles * pl.nseg;
+    // persistent: one CTA per SM (232448 bytes of shared memory each).  NCCL-overlapped slab interiors (fa.leave_sms) launch one
+    // CTA per item instead, so that SMs free up for the send/recv kernels of the halo stream (profiles/r1_tmarch.md)
+    const unsigned grid = (unsigned)((nitems < nsm || fa.leave_sms) ? nitems : nsm);
     TmMaps maps;
     const tm::Tables* tab = device_tables(dev);
     if (!tab || !tensor_maps_for(uin, g, swizzle, &maps)) return false;
@@ -691,11 +713,7 @@ bool launch_tmarch_fused(cudaStream_t st, const Geom& g, int t_begin, int t_coun
     ar.swz = swizzle ? 0x70u : 0u;
     ar.peer_prev = fa.do_exp ? fa.peer_prev : nullptr;
     ar.peer_next = fa.do_exp ? fa.peer_next : nullptr;
-    const long nitems = (long)pl.ntiles * pl.nseg;
-    // persistent: one CTA per SM (232448 bytes of shared memory each).  NCCL-overlapped slab interiors (fa.leave_sms) launch one
-    // CTA per item instead, so that SMs free up for the send/recv kernels of the halo stream (profiles/r1_tmarch.md)
-    const unsigned grid = (unsigned)((nitems < nsm || fa.leave_sms) ? nitems : nsm);
-#define GFB_LAUNCH_TM(R, W, E)                                                                                                  \
+#define GFB_LAUNCH_TM(R, W, E)                                                                                                 \
     do {                                                                                                                        \
         static bool attr_set[2][64] = {};  /* per device: one process may drive several GPUs */                                 \
         if (ws) {                                                                                                               \

@@ -61,6 +61,23 @@ struct Box {
     int base;          // byte offset inside its part (128-byte aligned)
 };
 
+// L2-blocked tile order: r in [0, ntx*nty*ntz) -> tile (tx, ty, tz).  Tiles are enumerated x fastest inside blocks of
+// ntx x by x bz tiles, blocks y fastest; the last block of a row / the last row are ragged when by, bz do not divide nty, ntz.
+// A bijection for any 1 <= by <= nty, 1 <= bz <= ntz (tests/host/tmarch_check.cpp).
+TM_HD void tile_of(int ntx, int nty, int ntz, int by, int bz, int r, int* tx, int* ty, int* tz) {
+    const int row = ntx * nty * bz;
+    const int zb = r / row;
+    r -= zb * row;
+    const int hz = (ntz - zb * bz) < bz ? (ntz - zb * bz) : bz;
+    const int blk = ntx * by * hz;
+    const int yb = r / blk;
+    r -= yb * blk;
+    const int hy = (nty - yb * by) < by ? (nty - yb * by) : by;
+    *tx = r % ntx;
+    r /= ntx;
+    *ty = yb * by + r % hy;
+    *tz = zb * bz + r / hy;
+}
 TM_HD int tile_extent(int d) { return d == 0 ? BX : d == 1 ? BY : BZ; }
 TM_HD int box_volume(const Box& b) { return b.e[0] * b.e[1] * b.e[2]; }
 TM_HD int pad128(int n) { return (n + 127) & ~127; }

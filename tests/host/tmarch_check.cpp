@@ -48,6 +48,19 @@ int main(int argc, char** argv) {
     // ring strides: multiples of 1024 bytes (the swizzle pattern must be the same in every slot), mbarriers in the tail of R slot 0
     if (S_SLOT % 1024 || R_SLOT % 1024 || S_SLOT < S_BYTES || R_SLOT < R_BYTES + 8 * 16 || SMEM_DATA != S_RING * S_SLOT + R_RING * R_SLOT ||
         SMEM_DATA > 232448 || BAR_OFF < S_RING * S_SLOT + R_BYTES || BAR_OFF + 8 * 16 > S_RING * S_SLOT + R_SLOT) { printf("ring layout\n"); return 1; }
+    // L2-blocked tile order (tile_of): a bijection onto the tile grid for every block shape, ragged blocks included
+    {
+        const int ntx = NXg / BX, nty = NYg / BY, ntz = NZg / BZ, nt3 = ntx * nty * ntz;
+        for (int by = 1; by <= nty; by++)
+            for (int bz = 1; bz <= ntz; bz++) {
+                std::vector<char> seen(nt3, 0);
+                for (int r = 0; r < nt3; r++) {
+                    int tx, ty, tz;
+                    tile_of(ntx, nty, ntz, by, bz, r, &tx, &ty, &tz);
+                    if (tx < 0 || tx >= ntx || ty < 0 || ty >= nty || tz < 0 || tz >= ntz || seen[(tz * nty + ty) * ntx + tx]++) { printf("tile_of by %d bz %d r %d\n", by, bz, r); return 1; }
+                }
+            }
+    }
     // shared memory (absolute byte address / 16) as 16-byte elements holding (link id * 9 + k); tile boxes are written the way
     // the 128-byte TMA swizzle writes them: chunk index (address bits 4-6) XOR address bits 7-9
     const bool swizzle = argc > 6 ? atoi(argv[6]) != 0 : true;
