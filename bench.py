@@ -1,33 +1,53 @@
 #!/usr/bin/env python
-"""bench.py -- SU(3) Wilson HMC MD steps/s on B200 (BASELINE.json metric) with roofline + CPU baseline.
+"""bench.py -- the SU(3) Wilson update loop on B200: MD steps/s (BASELINE.json metric) with roofline, CPU baseline, e2e.
 
-    python bench.py --gpus 1 --steps 20 --warmup 3
+    python bench.py --gpus 1 --steps 20 --warmup 3                       # default workload md64 (BASELINE.json configs[4])
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference --gpus N --steps K --warmup W     # CPU arm (oracle port; see DESIGN.md)
+    python bench.py --impl reference --gpus N --steps K --warmup W     # CPU arm (oracle port; see DESIGN.md section 7)
+    python bench.py --workload flow32  [--gpus N]                        # configs[2]: 32^4 RK3 Wilson flow with E(t) every step
+    python bench.py --workload stout48 [--gpus N]                        # configs[3]: 48^3x96 HMC, 2-layer stout-smeared Wilson action
+    python bench.py --workload md16                                      # configs[1]: 16^4 beta = 6.0 (L2-resident, no roofline claim)
 
-A "step" is one QPQ molecular-dynamics step (md_step!, src/molecular_dynamics.jl:611-616) of the
-quenched Wilson action over the whole lattice.  The timed region is ONE gfb_md_trajectory call of
-exactly K steps (diagnostics off), device-timed with CUDA events on the library's compute stream,
-bracketed by barrier + device synchronize, max over ranks.  Workload (BASELINE.json configs[4], the lattice the
-metric and the north-star target are quoted on): synthetic hot start (seed 1234), Gaussian momenta (seed 0x5678),
-beta = 6.2, GLOBAL lattice 64^4 split into t-slabs over the N GPUs (strong scaling; 64^4 fits one B200: 24 GB).
-`--scaling weak --lattice X,Y,Z,T` keeps X*Y*Z*T sites PER GPU instead.  The link field (9.7 GB / N per GPU) is larger
-than L2 (126 MB), so no flush is needed.
+Workloads (a "step" is one pass of the hot path over the whole lattice):
+  md64 / md16  one QPQ molecular-dynamics step (md_step!, src/molecular_dynamics.jl:611-616) of the quenched Wilson action.
+               The timed region is ONE gfb_md_trajectory call of exactly K steps (diagnostics off).
+  flow32       one Luescher RK3 flow step (flow!, src/smearing/gradientflow.jl:171-238) followed by the clover E(t)
+               measurement (samples/measurements/energydensity.jl:4-78), eps = 0.01.
+  stout48      one QPQ MD step of HMC with the action evaluated on 2-layer stout-smeared links, rho = 0.1, composed exactly as
+               the reference's user script does (test/HMCstout_test_nowing.jl:99-118): calc_smearedU, calc_dSdUmu, back_prop,
+               momentum kick, link update.
+All are device-timed with CUDA events on the library's compute stream, bracketed by barrier + device synchronize, max over
+ranks.  Synthetic hot start (seed 1234), Gaussian momenta (seed 0x5678); the global lattice is split into t-slabs over the N
+GPUs (strong scaling); `--scaling weak --lattice X,Y,Z,T` keeps X*Y*Z*T sites PER GPU.  The fields are larger than L2 (126 MB)
+except for md16, so no flush is needed (md16 says so in its config and makes no roofline claim).
 """
 import argparse
 import json
 import os
-import subprocess
 import sys
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "gaugefields.jl_b200"))
 
-METRIC = "SU(3) Wilson HMC MD steps/s"
-UNIT = "MD steps/s"
-U_BYTES, P_BYTES = 576, 256  # per site (SURVEY.md section 8)
+U_BYTES, P_BYTES = 576, 256  # per site (SURVEY.md section 8d)
+
+WORKLOADS = {
+    # name: (default lattice, default beta, metric, unit)
+    "md64": ("64,64,64,64", 6.2, "SU(3) Wilson HMC MD steps/s", "MD steps/s"),
+    "md16": ("16,16,16,16", 6.0, "SU(3) Wilson HMC MD steps/s", "MD steps/s"),
+    "flow32": ("32,32,32,32", 6.0, "SU(3) RK3 Wilson flow steps/s (with E(t))", "flow steps/s"),
+    "stout48": ("48,48,48,96", 6.0, "SU(3) stout-smeared (rho=0.1, 2 layers) Wilson HMC MD steps/s", "MD steps/s"),
+}
+FLOW_EPS, STOUT_RHO, STOUT_LAYERS = 0.01, 0.1, 2
+# algorithmic bytes per site of one step as executed: each field element moved once per kernel
+MD_STEP_BYTES = 2 * U_BYTES + 2 * P_BYTES                      # fused kick+drift: U r/w, P r/w = 1664
+FLOW_STEP_BYTES = (2 * U_BYTES + P_BYTES) + (2 * U_BYTES + 2 * P_BYTES) + (2 * U_BYTES + P_BYTES)  # 3 fused stages = 4480
+STOUT_FWD_BYTES = 2 * U_BYTES                                   # per layer, no tape
+STOUT_BWD_BYTES = 8 * U_BYTES                                   # per layer: (U, d_out -> Lambda, d_in) + (U, Lambda, d_in -> d_in)
+STOUT_STEP_BYTES = (STOUT_LAYERS * STOUT_FWD_BYTES + 2 * U_BYTES + STOUT_LAYERS * STOUT_BWD_BYTES + (2 * U_BYTES + 2 * P_BYTES)
+                    + (2 * U_BYTES + P_BYTES))                  # forward, dSdU, back_prop, kick, merged link update
 
 
 def parse():
@@ -36,14 +56,22 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--lattice", default="64,64,64,64", help="NX,NY,NZ,NT: the global lattice (strong) or the per-GPU lattice (weak)")
+    ap.add_argument("--workload", default="md64", choices=sorted(WORKLOADS))
+    ap.add_argument("--lattice", default=None, help="NX,NY,NZ,NT: the global lattice (strong) or the per-GPU lattice (weak)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
-    ap.add_argument("--beta", type=float, default=6.2)
+    ap.add_argument("--beta", type=float, default=None)
     ap.add_argument("--tau", type=float, default=1.0)
-    ap.add_argument("--unfused", action="store_true", help="issue the reference's op sequence (link, kick, link) per step")
+    ap.add_argument("--unfused", action="store_true", help="md*: issue the reference's op sequence (link, kick, link) per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-parity-check", action="store_true")
+    args = ap.parse_args()
+    lat, beta, _, _ = WORKLOADS[args.workload]
+    if args.lattice is None:
+        args.lattice = lat
+    if args.beta is None:
+        args.beta = beta
+    return args
 
 
 def measured_peak():
@@ -116,71 +144,157 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port timed on the host cores (the reference is pure Julia with un-vendored
-# dependencies and cannot be built here; DESIGN.md "Reference arm")
+# CPU arm: the oracle port timed on the host cores.  The reference is pure Julia with un-vendored
+# dependencies and cannot be built here, so kind = "port".
 # ------------------------------------------------------------------------------------------------
-def cpu_md_steps_per_s(dims_global, beta, tau, steps, warmup, budget_s):
+def _oracle(threads):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import gf_oracle as oracle
 
-    cores = os.cpu_count() or 1
-    v_full = 1
-    for d in dims_global:
-        v_full *= d
-    # probe on a 16^3 x 8 sample to decide whether the full lattice fits the time budget
-    probe = (16, 16, 16, 8)
-    Up = oracle.hot_start_philox(probe, 1234)
-    Pp = oracle.gaussian_momenta(probe, 0x5678, 0)
-    t0 = time.time()
-    oracle.md_step(Up, Pp, probe, beta, tau / max(steps, 1), 0)
-    t_probe = time.time() - t0
-    v_probe = 16 * 16 * 16 * 8
-    est_full = t_probe * v_full / v_probe
-    if est_full * (steps + warmup) <= budget_s:
-        dims, scale, sample = tuple(dims_global), 1.0, "full lattice %s, %d+%d QPQ steps" % ("x".join(map(str, dims_global)), warmup, steps)
-    else:
-        # bounded sample: a sub-volume with the same arithmetic per site, throughput scaled by the site ratio
-        dims = (16, 16, 16, 16)
-        while 16 * 16 * 16 * dims[3] * 2 <= v_full and t_probe * (16 * 16 * 16 * dims[3] * 2) / v_probe * (steps + warmup) <= budget_s:
-            dims = (16, 16, 16, dims[3] * 2)
-        v_s = dims[0] * dims[1] * dims[2] * dims[3]
-        scale = v_s / v_full
-        sample = "sub-volume %s of %s (per-site work identical; steps/s scaled by %d/%d sites), %d+%d QPQ steps" % (
-            "x".join(map(str, dims)), "x".join(map(str, dims_global)), v_s, v_full, warmup, steps)
+    oracle.build()
+    # torch.distributed.run exports OMP_NUM_THREADS=1; the oracle's thread count is set explicitly and read back
+    return oracle, oracle.threads(threads)
+
+
+def _oracle_step(oracle, workload, dims, beta, eps):
+    """One step of `workload` on the oracle: returns a closure over freshly initialised fields."""
     U = oracle.hot_start_philox(dims, 1234)
+    if workload == "flow32":
+        def step():
+            oracle.flow_step(U, dims, FLOW_EPS)
+            oracle.energy_density_clover(U, dims)
+        return step
     P = oracle.gaussian_momenta(dims, 0x5678, 0)
-    eps = tau / steps
+    if workload == "stout48":
+        def step():
+            oracle.update_links(U, P, dims, eps / 2)
+            tape, cur = [], U
+            for _ in range(STOUT_LAYERS):
+                tape.append(cur)
+                cur = oracle.stout_forward(cur, dims, STOUT_RHO)
+            d = oracle.wilson_dSdU(cur, dims, beta)
+            for inp in reversed(tape):
+                d = oracle.stout_backward(d, inp, dims, STOUT_RHO)
+            oracle.kick_from_dSdU(P, U, d, dims, -eps / 3.0)
+            oracle.update_links(U, P, dims, eps / 2)
+        return step
+    return lambda: oracle.md_step(U, P, dims, beta, eps, 0)
+
+
+def cpu_steps_per_s(workload, dims_global, beta, tau, steps, warmup, budget_s):
+    """`steps` timed steps (after `warmup`) of the oracle on a BOUNDED sample of the workload: the full lattice when
+    (steps + warmup) of them fit `budget_s`, otherwise a t-sub-volume NX x NY x NZ x T_s (identical arithmetic per site) whose
+    throughput is scaled by the site ratio -- stated in `sample` and flagged by `same_config`."""
+    cores = os.cpu_count() or 1
+    oracle, threads = _oracle(cores)
+    nx, ny, nz, nt = dims_global
+    v_full = nx * ny * nz * nt
+    eps = tau / max(steps, 1)
+    probe = (16, 16, 16, 4)
+    t0 = time.time()
+    _oracle_step(oracle, workload, probe, beta, eps)()
+    per_site = (time.time() - t0) / (16 * 16 * 16 * 4)
+    n = steps + warmup
+    if per_site * v_full * n <= budget_s:
+        dims = tuple(dims_global)
+    else:
+        ts = nt
+        while ts > 2 and per_site * nx * ny * nz * ts * n > budget_s:
+            ts //= 2
+        dims = (nx, ny, nz, max(ts, 2))
+        while per_site * dims[0] * dims[1] * dims[2] * dims[3] * n > budget_s and dims[0] > 8:
+            dims = (dims[0] // 2, dims[1] // 2, dims[2] // 2, dims[3])
+    v_s = dims[0] * dims[1] * dims[2] * dims[3]
+    same = v_s == v_full
+    step = _oracle_step(oracle, workload, dims, beta, eps)
     for _ in range(warmup):
-        oracle.md_step(U, P, dims, beta, eps, 0)
+        step()
     t0 = time.time()
     for _ in range(steps):
-        oracle.md_step(U, P, dims, beta, eps, 0)
+        step()
     dt = time.time() - t0
+    scale = v_s / v_full
     value = steps / dt * scale
-    return value, dt / steps * 1e3 / scale, {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    sample = ("full lattice %s, %d+%d steps" % ("x".join(map(str, dims_global)), warmup, steps)) if same else (
+        "sub-volume %s of %s (identical per-site arithmetic; steps/s scaled by %d/%d sites), %d+%d steps, %.1f s of CPU time" % (
+            "x".join(map(str, dims)), "x".join(map(str, dims_global)), v_s, v_full, warmup, steps, dt))
+    cb = {"value": value, "unit": WORKLOADS[workload][3], "cores": threads, "kind": "port", "sample": sample, "same_config": same,
+          "sample_ms_per_step": dt / steps * 1e3, "sample_sites": v_s,
+          "how": "oracle/gf_oracle.cpp (C++17/OpenMP restatement of the reference's serial math), %d OpenMP threads of %d host cores" % (threads, cores)}
+    return value, dt / steps * 1e3 / scale, cb
 
 
 def workload_name(args, dims_global, dims_local):
-    return "SU(3) Wilson QPQ HMC, beta=%g, hot start seed 1234, global lattice %s, %s scaling (%s per GPU, t-slabs)" % (
-        args.beta, "x".join(map(str, dims_global)), args.scaling, "x".join(map(str, dims_local)))
+    what = {"md64": "SU(3) Wilson QPQ HMC", "md16": "SU(3) Wilson QPQ HMC", "flow32": "SU(3) RK3 Wilson flow (eps=%g) + clover E(t) per step" % FLOW_EPS,
+            "stout48": "SU(3) QPQ HMC, Wilson action on %d-layer stout links (rho=%g)" % (STOUT_LAYERS, STOUT_RHO)}[args.workload]
+    return "%s, beta=%g, hot start seed 1234, global lattice %s, %s scaling (%s per GPU, t-slabs)" % (
+        what, args.beta, "x".join(map(str, dims_global)), args.scaling, "x".join(map(str, dims_local)))
 
 
 def run_reference(args, dims_global, dims_local, rank, world):
     if rank != 0:
         return
-    value, ms, cb = cpu_md_steps_per_s(dims_global, args.beta, args.tau, args.steps, args.warmup, budget_s=150.0)
+    _, _, metric, unit = WORKLOADS[args.workload]
+    value, ms, cb = cpu_steps_per_s(args.workload, dims_global, args.beta, args.tau, args.steps, args.warmup, budget_s=120.0)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args, dims_global, dims_local),
-                   "note": "CPU oracle port of the reference's serial math, all host cores (OpenMP); the reference is Julia + un-vendored "
-                           "LatticeMatrices.jl and cannot be built in this image (DESIGN.md section 7)"},
+                   "note": "CPU oracle port of the reference's serial math on all host cores (OpenMP); the reference is Julia + un-vendored "
+                           "LatticeMatrices.jl and cannot be built in this image (DESIGN.md section 7).  value/ms_per_step are the sample's "
+                           "throughput scaled to the full lattice when cpu_baseline.same_config is false"},
         "cpu_baseline": cb,
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# multi-GPU parity check (outside the timed region): the same slab code path as the benchmark on a small lattice the oracle
+# finishes in a blink; every rank compares ITS slab, the worst deviation over ranks is printed in the JSON line
+# ------------------------------------------------------------------------------------------------
+def parity_check(gfb200, backend, world, dist, torch):
+    import numpy as np
+
+    oracle, _ = _oracle(2)
+    dims, beta = (8, 4, 4, 4 * world), 5.7
+    Uh = oracle.hot_start_philox(dims, 1234)
+    for _ in range(2):
+        oracle.flow_step(Uh, dims, 0.02)
+    Ph = oracle.gaussian_momenta(dims, 0x5678, 2)
+    t0, t1 = backend.t_range(dims[3])
+    U = gfb200.gauge_configuration(dims, backend=backend).upload(Uh)
+    P = gfb200.gauge_momenta(U).upload(Ph)
+    loops = gfb200.make_loops_fromname("plaquette")
+    action = gfb200.GaugeAction(U).push(beta / 2, loops + loops.adjoint())
+    F = gfb200.gauge_momenta(U)
+    gfb200.md_force_(F, action, U)
+    Fw = oracle.force(Uh, dims, beta)
+    e_force = float(np.abs(F.to_host(local=True) - Fw[:, t0:t1]).max() / np.abs(Fw).max())
+    plaq, plaq_w = gfb200.calculate_Plaquette(U), oracle.plaquette_sum(Uh, dims)
+    md = gfb200.md_driver(U, action, steps=6, trajectory_length=0.3, integrator=gfb200.QPQ, fused=True)
+    res = gfb200.md_trajectory_(U, P, md)
+    Uo, Po = Uh.copy(), Ph.copy()
+    H0, H1 = oracle.md_trajectory(Uo, Po, dims, beta, 6, 0.3, 0)
+    e_links = float(np.abs(U.to_host(local=True) - Uo[:, t0:t1]).max())
+    U.upload(Uh)
+    gfb200.flow_(U, gfb200.gradient_flow(U, steps=2, step_size=0.01))
+    Uf = Uh.copy()
+    for _ in range(2):
+        oracle.flow_step(Uf, dims, 0.01)
+    e_flow = float(np.abs(U.to_host(local=True) - Uf[:, t0:t1]).max())
+    ee, ee_w = gfb200.energy_density(U), oracle.energy_density_clover(Uf, dims)
+    errs = [e_force, abs(plaq - plaq_w) / abs(plaq_w), abs(res.delta_hamiltonian - (H1 - H0)), e_links, e_flow, abs(ee - ee_w) / max(1.0, abs(ee_w))]
+    if dist is not None:
+        t = torch.tensor(errs, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        errs = [float(v) for v in t.tolist()]
+    tol = [1e-12, 1e-12, 1e-9, 1e-11, 1e-12, 1e-11]
+    names = ["force_rel", "plaquette_rel", "delta_H_abs", "links_after_trajectory_abs", "links_after_flow_abs", "energy_density_rel"]
+    return {"lattice": "x".join(map(str, dims)), "ranks": world, "checker": "oracle/gf_oracle.cpp", "max_over_ranks": dict(zip(names, errs)),
+            "tolerance": dict(zip(names, tol)), "ok": all(e <= t for e, t in zip(errs, tol))}
 
 
 def main():
@@ -197,6 +311,7 @@ def main():
             raise SystemExit("NT must be divisible by the number of GPUs")
         dims_global, tl = (nx, ny, nz, nt), nt // ngp
     dims_local = (nx, ny, nz, tl)
+    _, _, metric, unit = WORKLOADS[args.workload]
 
     if args.impl == "reference":
         run_reference(args, dims_global, dims_local, rank, world)
@@ -219,13 +334,14 @@ def main():
     K, W = args.steps, max(args.warmup, 3)
     sites_global = dims_global[0] * dims_global[1] * dims_global[2] * dims_global[3]
     sites_local = nx * ny * nz * tl
+    wl = args.workload
+    is_md = wl in ("md64", "md16")
 
     U = gfb200.gauge_configuration(dims_global, backend=backend, start="hot", seed=1234)
-    P = gfb200.gaussian_momenta(U, seed=0x5678, sweep=0)
+    P = gfb200.gaussian_momenta(U, seed=0x5678, sweep=0) if wl != "flow32" else None
     loops = gfb200.make_loops_fromname("plaquette")
     action = gfb200.GaugeAction(U).push(args.beta / 2, loops + loops.adjoint())
-    md = gfb200.md_driver(U, action, steps=K, trajectory_length=args.tau, integrator=gfb200.QPQ, fused=not args.unfused)
-    md_w = gfb200.md_driver(U, action, steps=1, trajectory_length=args.tau / K, integrator=gfb200.QPQ, fused=not args.unfused)
+    eps = args.tau / K
 
     def barrier():
         backend.sync()
@@ -233,18 +349,58 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- the step of each workload -----------------------------------------------------------------
+    energies = []
+    if is_md:
+        md = gfb200.md_driver(U, action, steps=K, trajectory_length=args.tau, integrator=gfb200.QPQ, fused=not args.unfused)
+        md_w = gfb200.md_driver(U, action, steps=1, trajectory_length=args.tau / K, integrator=gfb200.QPQ, fused=not args.unfused)
+
+        def warm():
+            gfb200.md_trajectory_(U, P, md_w, diagnostics=False)
+
+        def timed():
+            gfb200.md_trajectory_(U, P, md, diagnostics=False)
+    elif wl == "flow32":
+        g1 = gfb200.gradient_flow(U, steps=1, step_size=FLOW_EPS)
+
+        def warm():
+            gfb200.flow_(U, g1)
+            gfb200.energy_density(U)
+
+        def timed():
+            for _ in range(K):
+                gfb200.flow_(U, g1)
+                energies.append(gfb200.energy_density(U))
+    else:
+        smearing = gfb200.stout_smearing(U, rho=STOUT_RHO, layers=STOUT_LAYERS)
+        ws = gfb200.StoutWorkspace(U, smearing)
+
+        def stout_step():
+            # QPQ with adjacent half drifts merged over the trajectory, like the fused Wilson trajectory
+            gfb200.stout_force_(P, U, action, smearing, eps, workspace=ws)
+            gfb200.update_gaugefields_(U, P, eps)
+
+        def warm():
+            stout_step()
+
+        def timed():
+            gfb200.update_gaugefields_(U, P, eps / 2)
+            for k in range(K):
+                gfb200.stout_force_(P, U, action, smearing, eps, workspace=ws)
+                gfb200.update_gaugefields_(U, P, eps if k + 1 < K else eps / 2)
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     for _ in range(W):
-        gfb200.md_trajectory_(U, P, md_w, diagnostics=False)  # one untimed MD step each
+        warm()
     barrier()
-    # ---- timed region: exactly K MD steps --------------------------------------------------------
+    # ---- timed region: exactly K steps ---------------------------------------------------------------
     n0 = backend.kernel_launches()
     barrier()
     sampler.mark(True)
     backend.tic()
-    gfb200.md_trajectory_(U, P, md, diagnostics=False)
+    timed()
     ms = backend.toc()
     barrier()
     sampler.mark(False)
@@ -254,51 +410,87 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
-    # ---- dominant kernel: average duration of the fused kick+drift launch --------------------------
-    # the K-step trajectory is K fused passes plus one half-drift (update_links); time that one
-    # alone and subtract, so achieved = algorithmic bytes per launch / average launch duration
-    t_extra = 0.0
-    if not args.unfused:
-        reps = 5
+
+    # ---- dominant kernel: average launch duration measured live with CUDA events on the compute stream ----------
+    peak, peak_src = measured_peak()
+
+    def timed_ms(fn, reps):
         backend.tic()
         for _ in range(reps):
-            gfb200.update_gaugefields_(U, P, 1e-9)
-        t_extra = backend.toc() / reps
+            fn()
+        t = backend.toc() / reps
         barrier()
-    peak, peak_src = measured_peak()
-    if args.unfused:
-        kern, kern_bytes = "k_update_links + k_force_fused<kick> + k_update_links (whole QPQ step)", (2 * (P_BYTES + 2 * U_BYTES) + U_BYTES + 2 * P_BYTES)
-        kern_ms = ms / K
-    else:
-        tiled = nx % 8 == 0 and ny % 4 == 0 and nz % 2 == 0 and os.environ.get("GFB200_TMARCH", "1") != "0"
-        if world > 1 and tl - 2 < 8 and os.environ.get("GFB200_TMARCH", "1") != "2":
-            tiled = False  # short slab interiors stay in k_force_fused (csrc/tmarch.cu, launch_tmarch_fused)
-        kern = ("k_tmarch_fused<READ_Z,WRITE_Z,DO_EXP>" if tiled else "k_force_fused<READ_Z,WRITE_Z,DO_EXP>") + " (staple->TA force->momentum kick->exp(eps P) U)"
-        kern_bytes = 2 * U_BYTES + 2 * P_BYTES
-        kern_ms = max(ms - t_extra, 1e-9) / K
-    achieved = kern_bytes * sites_local / (kern_ms * 1e-3) / 1e9
+        return t
+
+    extra = {}
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    tj = {}
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
-            key = "k_tmarch_fused_bytes_per_site" if kern.startswith("k_tmarch") and "k_tmarch_fused_bytes_per_site" in tj else "k_force_fused_bytes_per_site"
-            traffic = tj[key] * sites_local  # ncu dram bytes per site (measured at tj["lattice"]) x this launch's sites
         except Exception:
-            traffic = None
+            tj = {}
+    if is_md:
+        if args.unfused:
+            kern, kern_bytes, kern_ms = "k_update_links + fused kick + k_update_links (whole QPQ step)", 3904, ms / K
+        else:
+            t_extra = timed_ms(lambda: gfb200.update_gaugefields_(U, P, 1e-9), 5)  # the trajectory's single half drift
+            tiled = nx % 8 == 0 and ny % 4 == 0 and nz % 2 == 0 and os.environ.get("GFB200_TMARCH", "1") != "0"
+            kern = ("k_tmarch_ws<READ_Z,WRITE_Z,DO_EXP>" if tiled else "k_force_fused<READ_Z,WRITE_Z,DO_EXP>") + " (staple->TA force->momentum kick->exp(eps P) U)"
+            kern_bytes, kern_ms = MD_STEP_BYTES, max(ms - t_extra, 1e-9) / K
+            key = "k_tmarch_ws" if tiled else "k_force_fused"
+            ent = tj.get(key, {}).get("x".join(map(str, dims_local)))
+            if ent:
+                traffic = ent["dram_bytes_per_site"] * sites_local
+                extra["traffic_source"] = ent.get("source")
+        step_bytes = MD_STEP_BYTES if not args.unfused else 3904
+    elif wl == "flow32":
+        gK = gfb200.gradient_flow(U, steps=K, step_size=FLOW_EPS)
+        t_flow = timed_ms(lambda: gfb200.flow_(U, gK), 1) / K
+        kern = "k_tmarch_ws<0,1,0> + <1,1,1> + <1,1,1> (the three RK3 stages: staple->TA->Z update->exp(c Z) U)"
+        kern_bytes, kern_ms = FLOW_STEP_BYTES, t_flow
+        extra["energy_density_ms"] = ms / K - t_flow
+        step_bytes = FLOW_STEP_BYTES + U_BYTES
+    else:
+        parts = gfb200.stout_force_(P, U, action, smearing, 1e-12, workspace=ws, timer=lambda fn: timed_ms(fn, 1))
+        t_link = timed_ms(lambda: gfb200.update_gaugefields_(U, P, 1e-12), 3)
+        parts["link_update"] = t_link
+        extra["parts_ms"] = parts
+        kern = "k_stout_lambda + k_stout_backward (back_prop through one stout layer)"
+        kern_bytes, kern_ms = STOUT_BWD_BYTES, parts["back_prop"] / STOUT_LAYERS
+        step_bytes = STOUT_STEP_BYTES
+    achieved = kern_bytes * sites_local / (kern_ms * 1e-3) / 1e9
 
-    # ---- e2e: the md_trajectory! call with HOST buffers (pinned), H2D + D2H inside the timed region ----
+    # ---- e2e: the same call with HOST buffers (pinned), H2D + D2H inside the timed region ---------------------------
     e2e = None
     if not args.no_e2e:
         Uh = gfb200.pinned_empty(U.local_shape(), np.complex128)  # each rank holds its own t-slab on the host
-        Ph = gfb200.pinned_empty(P.local_shape(), np.float64)
-        U.to_host(Uh, local=True); P.to_host(Ph, local=True)
-        md_e = gfb200.md_driver(U, action, steps=K, trajectory_length=args.tau, integrator=gfb200.QPQ, fused=not args.unfused)
+        U.to_host(Uh, local=True)
+        Ph = None
+        if P is not None:
+            Ph = gfb200.pinned_empty(P.local_shape(), np.float64)
+            P.to_host(Ph, local=True)
+        if is_md:
+            md_e = gfb200.md_driver(U, action, steps=K, trajectory_length=args.tau, integrator=gfb200.QPQ, fused=not args.unfused)
 
         def traj_e2e():
-            U.upload(Uh, local=True); P.upload(Ph, local=True)
-            res = gfb200.md_trajectory_(U, P, md_e, diagnostics=True)
-            U.to_host(Uh, local=True); P.to_host(Ph, local=True)
+            U.upload(Uh, local=True)
+            if P is not None:
+                P.upload(Ph, local=True)
+            if is_md:
+                res = gfb200.md_trajectory_(U, P, md_e, diagnostics=True).delta_hamiltonian
+            elif wl == "flow32":
+                for _ in range(K):
+                    gfb200.flow_(U, g1)
+                    res = gfb200.energy_density(U)
+            else:
+                h0 = gfb200.stout_hamiltonian(U, P, action, smearing, workspace=ws)
+                timed()
+                res = gfb200.stout_hamiltonian(U, P, action, smearing, workspace=ws) - h0
+            U.to_host(Uh, local=True)
+            if P is not None:
+                P.to_host(Ph, local=True)
             return res
 
         traj_e2e()
@@ -313,36 +505,47 @@ def main():
             t = torch.tensor([dt], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        bytes_dir = sites_local * (U_BYTES + P_BYTES) * world
-        e2e = {"value": K / dt, "unit": UNIT, "h2d_bytes_per_step": bytes_dir / K, "d2h_bytes_per_step": (bytes_dir + 16) / K,
-               "call": "upload U,P (pinned host, reference gathered layout) -> md_trajectory!(%d QPQ steps, diagnostics) -> download U,P" % K,
-               "delta_hamiltonian": res.delta_hamiltonian}
+        bytes_dir = sites_local * (U_BYTES + (P_BYTES if P is not None else 0)) * world
+        e2e = {"value": K / dt, "unit": unit, "h2d_bytes_per_step": bytes_dir / K, "d2h_bytes_per_step": (bytes_dir + 16) / K,
+               "call": "upload fields (pinned host, reference gathered layout) -> %d steps with diagnostics -> download fields" % K,
+               "result": res}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        _, _, cpu_baseline = cpu_md_steps_per_s(dims_global, args.beta, args.tau, 2, 1, budget_s=25.0)
+        _, _, cpu_baseline = cpu_steps_per_s(wl, dims_global, args.beta, args.tau, 2, 1, budget_s=20.0)
+
+    parity = None
+    if world > 1 and not args.no_parity_check:
+        parity = parity_check(gfb200, backend, world, dist, torch)
 
     if rank == 0:
-        step_bytes = (2 * U_BYTES + 2 * P_BYTES) if not args.unfused else 3904
         line = {
-            "metric": METRIC, "value": K / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "metric": metric, "value": K / (ms * 1e-3), "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": workload_name(args, dims_global, dims_local),
-                "integrator": "QPQ, %s" % ("reference op sequence (link, kick, link)" if args.unfused else "fused kick+drift kernel, adjacent half drifts merged"),
-                "l2": "inputs larger than L2 (links %.0f MB per GPU), no flush" % (sites_local * U_BYTES / 1e6),
+                "integrator": ("QPQ, %s" % ("reference op sequence (link, kick, link)" if args.unfused else "fused kick+drift kernel, adjacent half drifts merged")) if is_md
+                              else ("RK3 (W1, W2, W3 stages fused with their exponentials)" if wl == "flow32" else "QPQ, adjacent half drifts merged; smearing recomputed every force"),
+                "l2": ("inputs larger than L2 (links %.0f MB per GPU), no flush" % (sites_local * U_BYTES / 1e6)) if sites_local * U_BYTES > 2.6e8
+                      else "links %.0f MB per GPU fit L2: no roofline claim for this configuration" % (sites_local * U_BYTES / 1e6),
                 "link_updates_per_s": 4.0 * sites_global * K / (ms * 1e-3),
                 "algorithmic_bytes_per_site_per_step": step_bytes,
                 "hbm_roofline_frac_of_8TBs_per_gpu": step_bytes * sites_local / (ms / K * 1e-3) / 8e12,
+                "halo": os.environ.get("GFB200_HALO", "peer stores inside the fused kernels (NCCL send/recv when peer access is unavailable)") if world > 1 else None,
             },
-            "roofline": {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": kern_bytes * sites_local,
-                         "note": "FP64 issue and shared-memory reads co-limit this kernel (about 1.5 k FP64 instructions and 141 LDS.128 per link); DESIGN.md section 3a, profiles/r1_tmarch.md"},
+            "roofline": dict({"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                              "traffic": traffic, "peak_source": peak_src, "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": kern_bytes * sites_local,
+                              "note": "FP64 issue and shared-memory reads co-limit the fused kernel (about 1.5 k FP64 instructions and 137 LDS.128 per link); DESIGN.md section 3a, profiles/r2_tmarch.md"},
+                             **extra),
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,
             "gpu_launches": int(launches) * world,
             "clocks": clocks,
         }
+        if parity is not None:
+            line["parity_check"] = parity
+        if energies:
+            line["config"]["E_first_last"] = [energies[0], energies[-1]]
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

@@ -28,7 +28,7 @@ __all__ = [
     "md_step_", "update_gaugefields_", "update_momenta_", "md_force_", "gradient_flow", "flow_",
     "energy_density", "stout_smearing", "smear", "Philox4x32", "GfbError", "gauge_lattice_size",
     "gauge_num_colors", "gauge_process_grid", "download_configuration", "upload_configuration_",
-    "calc_smearedU", "back_prop", "calc_dSdU", "stout_force_", "evaluate_GaugeAction",
+    "calc_smearedU", "back_prop", "calc_dSdU", "stout_force_", "evaluate_GaugeAction", "StoutWorkspace", "stout_hamiltonian", "reunitarize_", "normalize_U_",
     "MatrixField", "link_field", "shift_U", "clear_U_", "unit_U_", "substitute_U_", "mul_", "add_U_", "tr",
     "Traceless_antihermitian_", "Traceless_antihermitian_add_", "exptU_",
 ]
@@ -407,6 +407,17 @@ def download_configuration(U):
     return U.to_host()
 
 
+def reunitarize_(U):
+    """normalize_U!(U) (src/4D/nowing/gaugefields_4D_nowing.jl:2387-2458): Gram-Schmidt rows 0, 1 and row 2 = conj(row0 x row1).
+    Call it after uploading a configuration that is unitary only to single precision (32-bit ILDG files): the fused passes use
+    their two-row SU(3) products only on configurations known to be unitary to 1e-12 and full 3x3 products otherwise."""
+    U.backend.call("gfb_reunitarize", U._h)
+    return U
+
+
+normalize_U_ = reunitarize_
+
+
 def gauge_momenta(U):
     """gauge_momenta(U) = initialize_TA_Gaugefields(U) (src/API.jl:331)."""
     return Momenta(U.backend, U.lattice)
@@ -707,15 +718,58 @@ def back_prop(dSdU, smearing, Uout_multi, Uin):
     return cur
 
 
-def stout_force_(P, U, action, smearing, step_size):
+class StoutWorkspace:
+    """Preallocated fields for the stout-smeared force (the reference allocates its layer outputs once in `calc_smearedU`'s
+    caller, test/HMCstout_test_nowing.jl:60-75): the layer outputs, dS/dU at the smeared links and the pulled-back derivatives."""
+
+    def __init__(self, U, smearing):
+        n = len(smearing.rhos)
+        self.outs = [GaugeConfiguration(U.backend, U.lattice) for _ in range(n)]
+        self.dS = GaugeConfiguration(U.backend, U.lattice)
+        self.prev = [GaugeConfiguration(U.backend, U.lattice) for _ in range(n)]
+
+
+def stout_force_(P, U, action, smearing, step_size, workspace=None, timer=None):
     """The momentum kick of HMC with a stout-smeared action as the user composes it in
     test/HMCstout_test_nowing.jl:99-118: Uout = calc_smearedU(U); dSdU = calc_dSdUμ(action, Uout);
-    dSdUbare = back_prop(dSdU); P_mu += -step_size/NC * TA(U_mu dSdUbare_mu)."""
-    Uout, multi = calc_smearedU(U, smearing)
-    dS = calc_dSdU(action, Uout)
-    bare = back_prop(dS, smearing, multi, U)
-    U.backend.call("gfb_kick_from_dSdU", P._h, U._h, bare._h, -float(step_size) / 3.0)
+    dSdUbare = back_prop(dSdU); P_mu += -step_size/NC * TA(U_mu dSdUbare_mu).
+    `workspace` (StoutWorkspace) avoids allocating seven configurations per call; `timer(fn) -> ms` (bench.py) runs each
+    stage through it and makes the call return {"forward", "dSdU", "back_prop", "kick"} in ms instead of P."""
+    ws = workspace if workspace is not None else StoutWorkspace(U, smearing)
+    be = U.backend
+    beta = action.wilson_beta()
+    inputs = [U] + ws.outs[:-1]
+
+    def forward():
+        for rho, inp, out in zip(smearing.rhos, inputs, ws.outs):
+            be.call("gfb_stout_forward", out._h, inp._h, rho, None)
+
+    def dsdu():
+        be.call("gfb_wilson_dSdU", ws.dS._h, ws.outs[-1]._h, beta)
+
+    def backward():
+        cur = ws.dS
+        for rho, inp, prev in zip(reversed(smearing.rhos), reversed(inputs), reversed(ws.prev)):
+            be.call("gfb_stout_backward", prev._h, cur._h, inp._h, rho)
+            cur = prev
+
+    def kick():
+        be.call("gfb_kick_from_dSdU", P._h, U._h, ws.prev[0]._h, -float(step_size) / 3.0)
+
+    if timer is not None:
+        return {"forward": timer(forward), "dSdU": timer(dsdu), "back_prop": timer(backward), "kick": timer(kick)}
+    forward(); dsdu(); backward(); kick()
     return P
+
+
+def stout_hamiltonian(U, P, action, smearing, workspace=None):
+    """H = S(smeared U) + p.p/2 for the stout-smeared action (test/HMCstout_test_nowing.jl:77-97)."""
+    ws = workspace if workspace is not None else StoutWorkspace(U, smearing)
+    inputs = [U] + ws.outs[:-1]
+    for rho, inp, out in zip(smearing.rhos, inputs, ws.outs):
+        U.backend.call("gfb_stout_forward", out._h, inp._h, rho, None)
+    # same convention as md_hamiltonian (molecular_dynamics.jl:494-505, :247-249): S = -(beta/NC) sum Re tr P
+    return -(action.wilson_beta() / 3.0) * calculate_Plaquette(ws.outs[-1]) + 0.5 * P.dot()
 
 
 # ------------------------------------------------------------------------------------------------

@@ -25,6 +25,8 @@
 //   momenta Float64[8,1,NX,NY,NZ,NT]                        (TA_gaugefields_4D_MPILattice.jl:34-35)
 // with the 4 directions stored back to back.
 
+#include <omp.h>
+
 #include <complex>
 #include <cmath>
 #include <cstdint>
@@ -319,6 +321,12 @@ inline M3 staple_sum(const double* U, const Lat& L, const int* x, int mu) {
 extern "C" {
 
 // ----------------------------------------------------------------------------- initial fields
+
+// threads the OpenMP loops below run on (bench.py reports it as cpu_baseline.cores); n > 0 sets it first
+int orc_threads(int n) {
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+}
 
 void orc_set_cold(double* U, const int* dims) {
     Lat L(dims);

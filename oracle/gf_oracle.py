@@ -42,6 +42,11 @@ def lib():
     return _LIB
 
 
+def threads(n=0):
+    """OpenMP threads of the oracle's loops; n > 0 sets the count first (torchrun exports OMP_NUM_THREADS=1)."""
+    return int(lib().orc_threads(int(n)))
+
+
 def _dp(a):
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
 

@@ -263,3 +263,47 @@ def test_argument_errors(backend):
         gfb200.update_gaugefields_(U, p, float("nan"), md)
     with pytest.raises(ValueError):
         backend.call("gfb_md_trajectory", U._h, p._h, 6.0, -1, 1.0, 0, 0, None)
+
+
+def test_non_unitary_links_take_the_full_product_path(backend, oracle):
+    """The fused kernels form staples from two rows of their (unitary) factors.  A configuration that is NOT unitary to 1e-12
+    -- e.g. a single-precision ILDG file, or any array a user uploads -- must still give the reference's numbers: the
+    reference's staples (src/AbstractGaugefields.jl:2041-2066) hold for arbitrary 3x3 matrices.  The library checks unitarity
+    once per uploaded configuration and switches every pass on it to full 3x3 products; gfb_reunitarize switches back."""
+    import gfb200
+
+    dims, beta = (8, 4, 2, 4), 5.8
+    rng = np.random.default_rng(7)
+    Uh = oracle.hot_start_philox(dims, 11)
+    Uh = Uh + 1e-7 * (rng.standard_normal(Uh.shape) + 1j * rng.standard_normal(Uh.shape))
+    U = gfb200.gauge_configuration(dims, backend=backend).upload(Uh)
+    loops = gfb200.make_loops_fromname("plaquette")
+    action = gfb200.GaugeAction(U).push(beta / 2, loops + loops.adjoint())
+    F = gfb200.gauge_momenta(U)
+    gfb200.md_force_(F, action, U)
+    want = oracle.force(Uh, dims, beta)
+    assert np.abs(F.to_host() - want).max() < 1e-12 * np.abs(want).max()
+    # the two-row shortcut would be off by ~1e-7 here: make sure this test can tell
+    Uu = Uh.copy()
+    oracle.reunitarize(Uu, dims)
+    assert np.abs(oracle.force(Uu, dims, beta) - want).max() > 1e-9 * np.abs(want).max()
+    # a fused trajectory on the non-unitary field follows the oracle (which multiplies whatever it is given)
+    Ph = oracle.gaussian_momenta(dims, 0x5678, 4)
+    P = gfb200.gauge_momenta(U).upload(Ph)
+    md = gfb200.md_driver(U, action, steps=4, trajectory_length=0.2, integrator=gfb200.QPQ, fused=True)
+    res = gfb200.md_trajectory_(U, P, md)
+    Uo, Po = Uh.copy(), Ph.copy()
+    H0, H1 = oracle.md_trajectory(Uo, Po, dims, beta, 4, 0.2, 0)
+    assert abs(res.delta_hamiltonian - (H1 - H0)) < 1e-9
+    assert np.abs(U.to_host() - Uo).max() < 1e-11
+    # the plaquette-staple stout layer and the flow as well
+    U.upload(Uh)
+    out = gfb200.smear(U, gfb200.stout_smearing(U, rho=0.1, layers=1))
+    assert np.abs(out.to_host() - oracle.stout_forward(Uh, dims, 0.1)).max() < 1e-12
+    # normalize_U! (reunitarize_) puts the configuration back on the fast path and on the group manifold
+    gfb200.reunitarize_(U)
+    got = U.to_host()
+    assert np.abs(got - Uu).max() < 1e-13
+    gfb200.md_force_(F, action, U)
+    wu = oracle.force(Uu, dims, beta)
+    assert np.abs(F.to_host() - wu).max() < 1e-12 * np.abs(wu).max()
