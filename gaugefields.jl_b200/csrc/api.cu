@@ -899,6 +899,84 @@ int gfb_hamiltonian(gfb_gauge* g, gfb_mom* p, double beta, double* out) {
     *out = -(beta / 3.0) * v[0] + 0.5 * v[1];
     return GFB_OK;
 }
+// [sum_{x, mu<nu} Re tr plaquette, sum_x Re tr of the 12 "rectangular" loops] (make_loops_fromname, wilsonloops.jl:233-245)
+int gfb_loop_sums(gfb_gauge* g, double* out2) {
+    if (!g || !out2) return fail(g ? g->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = g->ctx;
+    if (ctx->nslabs_total > 1) return fail(ctx, GFB_ERR_ARG, "rectangle loops need a halo of width 2: use a single-GPU context");
+    Slab& s = ctx->slabs[0];
+    Geom geo = geom_of(g, 0);
+    GFB_CHECK(ensure_partial(ctx, s, (size_t)plaquette_blocks(geo) * 2 + 16));
+    GFB_CUDA(ctx, cudaSetDevice(s.device));
+    int nb = 0;
+    launch_loop_sums(s.stream, geo, g->d[0], s.d_partial, &nb);
+    launch_final_reduce(s.stream, s.d_partial, nb, s.d_result);
+    launch_final_reduce(s.stream, s.d_partial + nb, nb, s.d_result + 1);
+    GFB_CHECK(post_launch(ctx, 3));
+    return gather_scalars(ctx, 2, out2);
+}
+
+// topological_charge_density / topological_charge (src/AbstractGaugefields.jl:1447-1490): method 0 plaquette, 1 clover,
+// 2 improved (5/3 clover - 1/12 rectangle).  The density lands in a device buffer in host order (x fastest, t slowest).
+static int topological_density(gfb_gauge* g, int method, std::vector<double*>& dens) {
+    gfb_ctx* ctx = g->ctx;
+    if (method < 0 || method > 2) return fail(ctx, GFB_ERR_ARG, "supported topological charge methods are plaquette (0), clover (1) and improved (2)");
+    if (method == 2 && ctx->nslabs_total > 1) return fail(ctx, GFB_ERR_ARG, "the improved topological charge uses rectangle loops (halo of width 2): use a single-GPU context");
+    GFB_CHECK(ensure_halo(g));
+    dens.assign(ctx->slabs.size(), nullptr);
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        Slab& s = ctx->slabs[i];
+        Geom geo = geom_of(g, i);
+        const size_t n = (size_t)geo.v3 * geo.tloc;
+        GFB_CHECK(ensure_staging(ctx, s, n * sizeof(double)));
+        GFB_CUDA(ctx, cudaSetDevice(s.device));
+        dens[i] = reinterpret_cast<double*>(s.d_staging);
+        if (method == 2) {
+            launch_topological_density(s.stream, geo, g->d[i], dens[i], 1, 5.0 / 3.0, false);
+            launch_topological_density(s.stream, geo, g->d[i], dens[i], 2, -1.0 / 12.0, true);
+            GFB_CHECK(post_launch(ctx, 2));
+        } else {
+            launch_topological_density(s.stream, geo, g->d[i], dens[i], method, 1.0, false);
+            GFB_CHECK(post_launch(ctx));
+        }
+    }
+    return GFB_OK;
+}
+int gfb_topological_charge(gfb_gauge* g, int method, double* out) {
+    if (!g || !out) return fail(g ? g->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = g->ctx;
+    std::vector<double*> dens;
+    GFB_CHECK(topological_density(g, method, dens));
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        Slab& s = ctx->slabs[i];
+        Geom geo = geom_of(g, i);
+        GFB_CHECK(ensure_partial(ctx, s, 1024 + 16));
+        GFB_CUDA(ctx, cudaSetDevice(s.device));
+        int nb = 0;
+        launch_sum_plain(s.stream, dens[i], (size_t)geo.v3 * geo.tloc, s.d_partial, &nb);
+        launch_final_reduce(s.stream, s.d_partial, nb, s.d_result);
+        GFB_CHECK(post_launch(ctx, 2));
+    }
+    return gather_scalars(ctx, 1, out);
+}
+// host_density: NX*NY*NZ*NT doubles, x fastest (the reference's density[ix, iy, iz, it]); a rank of a one-process-per-GPU
+// context passes the global array and fills only its own time-slices
+int gfb_topological_charge_density(gfb_gauge* g, int method, double* host_density) {
+    if (!g || !host_density) return fail(g ? g->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = g->ctx;
+    std::vector<double*> dens;
+    GFB_CHECK(topological_density(g, method, dens));
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        Slab& s = ctx->slabs[i];
+        Geom geo = geom_of(g, i);
+        const size_t n = (size_t)geo.v3 * geo.tloc;
+        GFB_CUDA(ctx, cudaSetDevice(s.device));
+        GFB_CUDA(ctx, cudaMemcpyAsync(host_density + (size_t)geo.v3 * geo.t0, dens[i], n * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+        GFB_CUDA(ctx, cudaStreamSynchronize(s.stream));
+    }
+    return GFB_OK;
+}
+
 int gfb_energy_density(gfb_gauge* g, int kind, double* out) {
     if (!g || !out) return fail(g ? g->ctx : nullptr, GFB_ERR_ARG, "null argument");
     gfb_ctx* ctx = g->ctx;
@@ -1006,6 +1084,16 @@ static int links_are_unitary(gfb_gauge* g, bool* yes) {
 static int fused_pass(gfb_gauge* g, const std::vector<double2*>& uin, const std::vector<double2*>* uout, const std::vector<double*>* zin,
                       const std::vector<double*>* zout, FusedArgs fa) {
     gfb_ctx* ctx = g->ctx;
+    if (fa.c_rect != 0.0) {
+        // rectangle staples reach two sites away: the t-slab halo is one slice wide, so this path is single-slab
+        if (ctx->nslabs_total > 1) return fail(ctx, GFB_ERR_ARG, "actions with rectangle terms need a halo of width 2: use a single-GPU context");
+        Slab& s = ctx->slabs[0];
+        GFB_CUDA(ctx, cudaSetDevice(s.device));
+        launch_force_general(s.stream, geom_of(g, 0), uin[0], uout ? (*uout)[0] : nullptr, zin ? (*zin)[0] : nullptr, zout ? (*zout)[0] : nullptr, fa);
+        return post_launch(ctx);
+    }
+    fa.a *= fa.c_plaq;  // plaquette-only actions: the coefficient folds into the force scale and the Wilson kernels run
+    fa.c_plaq = 1.0;
     bool unitary = true;
     GFB_CHECK(links_are_unitary(g, &unitary));
     fa.full3 = !unitary;
@@ -1118,7 +1206,24 @@ int gfb_exp_aF_U(gfb_gauge* w, double a, const gfb_mom* f, const gfb_gauge* u) {
     return GFB_OK;
 }
 
-int gfb_md_trajectory(gfb_gauge* g, gfb_mom* p, double beta, int steps, double tau, int integrator, int fused, double* H) {
+// S = -(2/NC) (c_plaq sum Re tr plaquettes + c_rect sum Re tr rectangles): the potential of a GaugeAction with the terms
+// (c_plaq, plaquette + plaquette') and (c_rect, rectangular + rectangular') (md_potential, molecular_dynamics.jl:247-249)
+static int hamiltonian_general(gfb_gauge* g, gfb_mom* p, double c_plaq, double c_rect, double* out) {
+    if (c_rect == 0.0) return gfb_hamiltonian(g, p, 2.0 * c_plaq, out);
+    double ls[2], kin = 0.0;
+    GFB_CHECK(gfb_loop_sums(g, ls));
+    GFB_CHECK(gfb_kinetic(p, &kin));
+    *out = -(2.0 / 3.0) * (c_plaq * ls[0] + c_rect * ls[1]) + 0.5 * kin;
+    return GFB_OK;
+}
+static int update_momenta_general(gfb_mom* p, gfb_gauge* g, double eps, double c_plaq, double c_rect) {
+    FusedArgs fa;
+    fa.a = eps * (-1.0 / 3.0); fa.b = 1.0; fa.read_z = true; fa.write_z = true;
+    fa.c_plaq = c_plaq; fa.c_rect = c_rect;
+    GFB_CHECK(ensure_halo(g));
+    return fused_pass(g, g->d, nullptr, &p->d, &p->d, fa);
+}
+static int md_trajectory_impl(gfb_gauge* g, gfb_mom* p, double c_plaq, double c_rect, int steps, double tau, int integrator, int fused, double* H) {
     if (!p || !g) return fail(g ? g->ctx : nullptr, GFB_ERR_ARG, "null argument");
     gfb_ctx* ctx = g->ctx;
     if (!same_shape(g, p)) return fail(ctx, GFB_ERR_ARG, "U and P must have the same lattice");
@@ -1126,18 +1231,18 @@ int gfb_md_trajectory(gfb_gauge* g, gfb_mom* p, double beta, int steps, double t
     if (!std::isfinite(tau)) return fail(ctx, GFB_ERR_ARG, "trajectory_length must be finite");
     if (tau == 0.0) return fail(ctx, GFB_ERR_ARG, "trajectory_length must not be zero");
     if (integrator != GFB_QPQ && integrator != GFB_PQP) return fail(ctx, GFB_ERR_ARG, "integrator must be QPQ or PQP");
-    if (H) GFB_CHECK(gfb_hamiltonian(g, p, beta, &H[0]));
+    if (H) GFB_CHECK(hamiltonian_general(g, p, c_plaq, c_rect, &H[0]));
     const double eps = tau / steps;
     if (!fused) {
         for (int k = 0; k < steps; k++) {
             if (integrator == GFB_QPQ) {
                 GFB_CHECK(gfb_update_links(g, p, eps / 2));
-                GFB_CHECK(gfb_update_momenta(p, g, eps, beta));
+                GFB_CHECK(update_momenta_general(p, g, eps, c_plaq, c_rect));
                 GFB_CHECK(gfb_update_links(g, p, eps / 2));
             } else {
-                GFB_CHECK(gfb_update_momenta(p, g, eps / 2, beta));
+                GFB_CHECK(update_momenta_general(p, g, eps / 2, c_plaq, c_rect));
                 GFB_CHECK(gfb_update_links(g, p, eps));
-                GFB_CHECK(gfb_update_momenta(p, g, eps / 2, beta));
+                GFB_CHECK(update_momenta_general(p, g, eps / 2, c_plaq, c_rect));
             }
         }
     } else {
@@ -1145,8 +1250,9 @@ int gfb_md_trajectory(gfb_gauge* g, gfb_mom* p, double beta, int steps, double t
         // adjacent half drifts (QPQ) / half kicks (PQP) of consecutive steps merged
         gfb_gauge_ws* ws = nullptr;
         GFB_CHECK(get_ws(g, true, false, &ws));
-        const double kf = -beta / 6.0;
+        const double kf = -1.0 / 3.0;
         FusedArgs fa;
+        fa.c_plaq = c_plaq; fa.c_rect = c_rect;
         fa.b = 1.0; fa.read_z = true; fa.write_z = true; fa.do_exp = true;
         if (integrator == GFB_QPQ) {
             GFB_CHECK(gfb_update_links(g, p, eps / 2));
@@ -1167,14 +1273,42 @@ int gfb_md_trajectory(gfb_gauge* g, gfb_mom* p, double beta, int steps, double t
                 std::swap(g->d, ws->alt);
                 g->halo_valid = true;  // exchanged inside the pass, overlapped with the interior slices
             }
-            GFB_CHECK(gfb_update_momenta(p, g, eps / 2, beta));
+            GFB_CHECK(update_momenta_general(p, g, eps / 2, c_plaq, c_rect));
         }
     }
-    if (H) GFB_CHECK(gfb_hamiltonian(g, p, beta, &H[1]));
+    if (H) GFB_CHECK(hamiltonian_general(g, p, c_plaq, c_rect, &H[1]));
     return GFB_OK;
 }
 
-int gfb_flow(gfb_gauge* g, double eps, int nsteps) {
+int gfb_md_trajectory(gfb_gauge* g, gfb_mom* p, double beta, int steps, double tau, int integrator, int fused, double* H) {
+    return md_trajectory_impl(g, p, beta / 2.0, 0.0, steps, tau, integrator, fused, H);
+}
+int gfb_md_trajectory_general(gfb_gauge* g, gfb_mom* p, double c_plaq, double c_rect, int steps, double tau, int integrator, int fused, double* H) {
+    return md_trajectory_impl(g, p, c_plaq, c_rect, steps, tau, integrator, fused, H);
+}
+int gfb_force_general(gfb_mom* f, gfb_gauge* g, double c_plaq, double c_rect) {
+    if (!f || !g) return fail(g ? g->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    if (!same_shape(g, f)) return fail(g->ctx, GFB_ERR_ARG, "force and U must have the same lattice");
+    GFB_CHECK(ensure_halo(g));
+    FusedArgs fa;
+    fa.a = -1.0 / 3.0;  // -(1/NC)
+    fa.write_z = true;
+    fa.c_plaq = c_plaq; fa.c_rect = c_rect;
+    return fused_pass(g, g->d, nullptr, nullptr, &f->d, fa);
+}
+int gfb_update_momenta_general(gfb_mom* p, gfb_gauge* g, double eps, double c_plaq, double c_rect) {
+    if (!p || !g) return fail(g ? g->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    if (!same_shape(g, p)) return fail(g->ctx, GFB_ERR_ARG, "P and U must have the same lattice");
+    if (!std::isfinite(eps)) return fail(g->ctx, GFB_ERR_ARG, "the momentum step size must be finite");
+    return update_momenta_general(p, g, eps, c_plaq, c_rect);
+}
+int gfb_hamiltonian_general(gfb_gauge* g, gfb_mom* p, double c_plaq, double c_rect, double* out) {
+    if (!g || !p || !out) return fail(g ? g->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    if (!same_shape(g, p)) return fail(g->ctx, GFB_ERR_ARG, "U and p must have the same lattice");
+    return hamiltonian_general(g, p, c_plaq, c_rect, out);
+}
+
+static int flow_impl(gfb_gauge* g, double eps, int nsteps, double c_plaq, double c_rect) {
     if (!g) return fail(nullptr, GFB_ERR_ARG, "null argument");
     gfb_ctx* ctx = g->ctx;
     if (nsteps <= 0) return fail(ctx, GFB_ERR_ARG, "steps must be positive");
@@ -1188,6 +1322,7 @@ int gfb_flow(gfb_gauge* g, double eps, int nsteps) {
     for (int k = 0; k < nsteps; k++) {
         FusedArgs fa;
         fa.write_z = true; fa.do_exp = true;
+        fa.c_plaq = c_plaq; fa.c_rect = c_rect;
         GFB_CHECK(ensure_halo(g));
         fa.a = -eps; fa.b = 0.0; fa.c = 0.25; fa.read_z = false;
         GFB_CHECK(fused_pass(g, g->d, &ws->alt, nullptr, &ws->z, fa));
@@ -1203,6 +1338,10 @@ int gfb_flow(gfb_gauge* g, double eps, int nsteps) {
     }
     return GFB_OK;
 }
+int gfb_flow(gfb_gauge* g, double eps, int nsteps) { return flow_impl(g, eps, nsteps, 1.0, 0.0); }
+// flow!(U, ::Gradientflow_general) (src/smearing/gradientflow.jl:240-316) for link values (c_plaq, c_rect) of the loop sets
+// ("plaquette", "rectangular"): F = TAcoeffs(U dSdU), the same RK3 scheme; (1, 0) is the Wilson flow
+int gfb_flow_general(gfb_gauge* g, double eps, int nsteps, double c_plaq, double c_rect) { return flow_impl(g, eps, nsteps, c_plaq, c_rect); }
 
 int gfb_stout_forward(gfb_gauge* out, gfb_gauge* in, double rho, gfb_mom* q) {
     if (!out || !in) return fail(in ? in->ctx : nullptr, GFB_ERR_ARG, "null argument");

@@ -149,13 +149,22 @@ struct FusedArgs {
     double2* peer_prev = nullptr;
     double2* peer_next = nullptr;
     bool full3 = false;      // links not unitary to 1e-12: full 3x3 products (k_force_fused only, as the reference's staples)
-    bool leave_sms = false;  // NCCL-overlapped slab interior: one CTA per item instead of a persistent grid, so the send/recv kernels get SMs
+    bool leave_sms = false;
+    // general-action path (general.cu): V = c_plaq V_plaq + c_rect V_rect; c_rect != 0 selects k_force_general
+    double c_plaq = 1.0, c_rect = 0.0;  // NCCL-overlapped slab interior: one CTA per item instead of a persistent grid, so the send/recv kernels get SMs
 };
 void launch_force_fused(cudaStream_t st, const Geom& g, int t_begin, int t_count, const double2* uin, double2* uout, const double* zin, double* zout,
                         const FusedArgs& fa);
 // persistent t-marching shared-memory variant of launch_force_fused (tmarch.cu); false = launch not covered, nothing launched
 bool launch_tmarch_fused(cudaStream_t st, const Geom& g, int t_begin, int t_count, const double2* uin, double2* uout, const double* zin, double* zout,
                          const FusedArgs& fa);
+// general-action path (general.cu): single-slab geometries only
+void launch_force_general(cudaStream_t st, const Geom& g, const double2* uin, double2* uout, const double* zin, double* zout, const FusedArgs& fa);
+// partial[0..nb) = block sums of sum_{mu<nu} Re tr P, partial[nb..2nb) = block sums of Re tr over the 12 rectangle loops
+void launch_loop_sums(cudaStream_t st, const Geom& g, const double2* u, double* partial, int* nblocks);
+// kind 0 plaquette, 1 clover, 2 rectangle field strengths; density[x + nx*(y + ny*(z + nz*t))] (+)= weight * q(x)
+void launch_topological_density(cudaStream_t st, const Geom& g, const double2* u, double* density, int kind, double weight, bool accumulate);
+void launch_sum_plain(cudaStream_t st, const double* v, size_t n, double* partial, int* nblocks);
 // peer-store halo exchange: tell both ring neighbours that pass `serial` is complete here, then wait for theirs
 void launch_halo_signal_wait(cudaStream_t st, unsigned* peer_flag_prev, unsigned* peer_flag_next, unsigned* my_flags, unsigned serial);
 // max over the local links of |U U^dag - 1|_max and |det U - 1| -> partial[0..nblocks) (block maxima)

@@ -64,6 +64,15 @@ SIGNATURES = {
     "gfb_stout_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_double]),
     "gfb_kick_from_dSdU": (c_int, [c_void_p, c_void_p, c_void_p, c_double]),
     "gfb_wilson_dSdU": (c_int, [c_void_p, c_void_p, c_double]),
+    # general-action path and topological charge
+    "gfb_loop_sums": (c_int, [c_void_p, P(c_double)]),
+    "gfb_force_general": (c_int, [c_void_p, c_void_p, c_double, c_double]),
+    "gfb_update_momenta_general": (c_int, [c_void_p, c_void_p, c_double, c_double, c_double]),
+    "gfb_hamiltonian_general": (c_int, [c_void_p, c_void_p, c_double, c_double, P(c_double)]),
+    "gfb_md_trajectory_general": (c_int, [c_void_p, c_void_p, c_double, c_double, c_int, c_double, c_int, c_int, P(c_double)]),
+    "gfb_flow_general": (c_int, [c_void_p, c_double, c_int, c_double, c_double]),
+    "gfb_topological_charge": (c_int, [c_void_p, c_int, P(c_double)]),
+    "gfb_topological_charge_density": (c_int, [c_void_p, c_int, c_void_p]),
     # primitive table
     "gfb_field_alloc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, P(c_void_p)]),
     "gfb_field_view": (c_int, [c_void_p, c_int, P(c_void_p)]),

@@ -28,7 +28,8 @@ __all__ = [
     "md_step_", "update_gaugefields_", "update_momenta_", "md_force_", "gradient_flow", "flow_",
     "energy_density", "stout_smearing", "smear", "Philox4x32", "GfbError", "gauge_lattice_size",
     "gauge_num_colors", "gauge_process_grid", "download_configuration", "upload_configuration_",
-    "calc_smearedU", "back_prop", "calc_dSdU", "stout_force_", "evaluate_GaugeAction", "StoutWorkspace", "stout_hamiltonian", "reunitarize_", "normalize_U_",
+    "calc_smearedU", "back_prop", "calc_dSdU", "stout_force_", "evaluate_GaugeAction", "StoutWorkspace", "stout_hamiltonian", "reunitarize_", "normalize_U_", "MDActionSet", "MDForceGroup", "SextonWeingarten",
+    "Gradientflow_general", "topological_charge", "topological_charge_density",
     "MatrixField", "link_field", "shift_U", "clear_U_", "unit_U_", "substitute_U_", "mul_", "add_U_", "tr",
     "Traceless_antihermitian_", "Traceless_antihermitian_add_", "exptU_",
 ]
@@ -482,19 +483,21 @@ class _Loops:
 
 
 def make_loops_fromname(name, Dim=4):
-    """make_loops_fromname("plaquette", Dim=4) (Wilsonloop.jl; used at docs/src/hmc.md:146-150)."""
+    """make_loops_fromname("plaquette" | "rectangular", Dim=4) (Wilsonloop.jl; docs/src/hmc.md:146-150,
+    docs/src/wilsonloops_actions.md:27): the six plaquettes / the twelve 1x2 and 2x1 rectangles of the mu < nu planes."""
     if Dim != 4:
         raise ValueError("the B200 backend supports Dim=4")
-    if name != "plaquette":
-        raise NotImplementedError("only the plaquette loop set is fused on the B200 backend; got %r" % (name,))
-    return _Loops([("plaquette", False)])
+    if name not in ("plaquette", "rectangular"):
+        raise NotImplementedError("the B200 backend builds the plaquette and rectangular loop sets; got %r" % (name,))
+    return _Loops([(name, False)])
 
 
 class GaugeAction:
     """GaugeAction(U) + push!(action, coefficient, loops) (src/action/GaugeActions.jl:20-62).
 
-    Only the Wilson action (plaquette union plaquette') takes the fused kernels, with
-    beta = 2 * coefficient.
+    Terms are (real coefficient, loops + loops') with loops = "plaquette" or "rectangular"; the plaquette-only action
+    (Wilson, beta = 2 * coefficient) runs the t-marching kernels, an action with a rectangle term the general-action
+    kernels (csrc/general.cu).
     """
 
     def __init__(self, U):
@@ -505,30 +508,92 @@ class GaugeAction:
         self.terms.append((complex(coefficient), loops))
         return self
 
-    def wilson_beta(self):
-        beta = 0.0
-        for coeff, loops in self.terms:
-            kinds = sorted(loops.names)
-            if kinds != [("plaquette", False), ("plaquette", True)]:
-                raise NotImplementedError(
-                    "the B200 backend fuses only plaquette+plaquette' actions; push!(action, beta/2, [plaq; plaq'])"
-                )
-            beta += 2.0 * coeff.real
+    def coefficients(self):
+        """(c_plaq, c_rect): the summed coefficients of the plaquette and rectangle terms."""
         if not self.terms:
             raise ValueError("the action has no terms")
-        return beta
+        c = {"plaquette": 0.0, "rectangular": 0.0}
+        for coeff, loops in self.terms:
+            kinds = sorted(loops.names)
+            if len(kinds) != 2 or kinds[0][0] != kinds[1][0] or [d for _, d in kinds] != [False, True]:
+                raise NotImplementedError("push!(action, coefficient, [loops; loops']) with loops = plaquette or rectangular")
+            if coeff.imag != 0.0:
+                raise NotImplementedError("complex loop coefficients are not fused on the B200 backend")
+            c[kinds[0][0]] += coeff.real
+        return c["plaquette"], c["rectangular"]
+
+    def wilson_beta(self):
+        cp, cr = self.coefficients()
+        if cr != 0.0:
+            raise NotImplementedError("this call takes the Wilson action only (plaquette + plaquette' terms)")
+        return 2.0 * cp
 
 
 def evaluate_GaugeAction(action, U):
-    """evaluate_GaugeAction (GaugeActions.jl:132-142): beta * sum_{x,mu<nu} Re tr P for the Wilson action."""
-    v = ctypes.c_double()
-    U.backend.call("gfb_wilson_action", U._h, action.wilson_beta(), ctypes.byref(v))
-    return complex(v.value, 0.0)
+    """evaluate_GaugeAction (GaugeActions.jl:132-142): sum over terms of coefficient * sum_x tr(loops + loops')
+    = 2 (c_plaq sum Re tr P + c_rect sum Re tr R); beta * sum Re tr P for the Wilson action."""
+    cp, cr = action.coefficients()
+    if cr == 0.0:
+        v = ctypes.c_double()
+        U.backend.call("gfb_wilson_action", U._h, 2.0 * cp, ctypes.byref(v))
+        return complex(v.value, 0.0)
+    v = (ctypes.c_double * 2)()
+    U.backend.call("gfb_loop_sums", U._h, v)
+    return complex(2.0 * (cp * v[0] + cr * v[1]), 0.0)
 
 
 # ------------------------------------------------------------------------------------------------
 # molecular dynamics (src/molecular_dynamics.jl)
 # ------------------------------------------------------------------------------------------------
+class MDActionSet:
+    """MDActionSet(; name = action, ...) (src/molecular_dynamics.jl:57-69): named action providers whose forces add."""
+
+    def __init__(self, **terms):
+        if not terms:
+            raise ValueError("an MDActionSet must contain at least one action provider")
+        self.terms = dict(terms)
+
+    def coefficients(self, names=None):
+        cp = cr = 0.0
+        for n in (self.terms if names is None else names):
+            if n not in self.terms:
+                raise ValueError("the action set has no member %r" % (n,))
+            a, b = self.terms[n].coefficients()
+            cp, cr = cp + a, cr + b
+        return cp, cr
+
+
+class MDForceGroup:
+    """MDForceGroup(names...) (src/molecular_dynamics.jl:78-92)."""
+
+    def __init__(self, *names):
+        if len(names) == 1 and isinstance(names[0], (tuple, list)):
+            names = tuple(names[0])
+        if not names:
+            raise ValueError("an MDForceGroup must contain at least one action name")
+        if len(set(names)) != len(names):
+            raise ValueError("an MDForceGroup must not contain duplicate action names: %s" % (names,))
+        self.names = tuple(names)
+
+
+def _force_group(g):
+    return g if isinstance(g, MDForceGroup) else MDForceGroup(g)
+
+
+class SextonWeingarten:
+    """SextonWeingarten(; fast, slow, n_fast, ordering=QPQ()) nested leapfrog (src/molecular_dynamics.jl:355-410, 618-700)."""
+
+    def __init__(self, fast, slow, n_fast, ordering=QPQ):
+        if int(n_fast) <= 0:
+            raise ValueError("n_fast must be positive; got %s" % (n_fast,))
+        self.fast, self.slow, self.n_fast = _force_group(fast), _force_group(slow), int(n_fast)
+        self.ordering = ordering if isinstance(ordering, type) else type(ordering)
+        if self.ordering not in (QPQ, PQP):
+            raise ValueError("ordering must be QPQ or PQP")
+        if set(self.fast.names) & set(self.slow.names):
+            raise ValueError("an action must not be in both the fast and the slow group")
+
+
 class MDDriver:
     """Preallocated deterministic MD driver (src/molecular_dynamics.jl:413-423)."""
 
@@ -536,11 +601,13 @@ class MDDriver:
         self.action, self.integrator = action, integrator
         self.trajectory_length, self.steps = float(trajectory_length), int(steps)
         self.force, self.fused = force, bool(fused)
-        self.beta = action.wilson_beta()
+        self.c_plaq, self.c_rect = action.coefficients()
+        self.beta = 2.0 * self.c_plaq if self.c_rect == 0.0 else None
 
 
 def md_driver(U, action, steps=None, trajectory_length=1.0, integrator=QPQ, fused=True):
     """md_driver(U, action; steps, trajectory_length=1.0, integrator=QPQ()) (src/molecular_dynamics.jl:440-483).
+    `action` is a GaugeAction or an MDActionSet; `integrator` QPQ, PQP or a SextonWeingarten instance.
 
     `fused=True` (default) runs each kick together with the following link update in one kernel
     and merges adjacent half link updates; `fused=False` issues the reference's op sequence.
@@ -553,6 +620,13 @@ def md_driver(U, action, steps=None, trajectory_length=1.0, integrator=QPQ, fuse
         raise ValueError("trajectory_length must be finite; got %s" % trajectory_length)
     if trajectory_length == 0:
         raise ValueError("trajectory_length must not be zero")
+    if isinstance(integrator, SextonWeingarten):
+        if not isinstance(action, MDActionSet):
+            raise ValueError("SextonWeingarten selects named members of an MDActionSet")
+        for n in integrator.fast.names + integrator.slow.names:
+            if n not in action.terms:
+                raise ValueError("the action set has no member %r" % (n,))
+        return MDDriver(action, integrator, trajectory_length, steps, gauge_momenta(U), fused)
     integ = integrator if isinstance(integrator, type) else type(integrator)
     if integ not in (QPQ, PQP):
         raise ValueError("md_step! is not implemented for %r" % (integrator,))
@@ -564,9 +638,10 @@ def md_step_size(driver):
 
 
 def md_hamiltonian(U, p, driver):
-    """md_hamiltonian (src/molecular_dynamics.jl:494-505): -(beta/3) sum Re tr P + p*p/2."""
+    """md_hamiltonian (src/molecular_dynamics.jl:494-505): -(1/NC) Re evaluate_GaugeAction + p*p/2
+    (= -(beta/3) sum Re tr P + p*p/2 for the Wilson action)."""
     v = ctypes.c_double()
-    U.backend.call("gfb_hamiltonian", U._h, p._h, driver.beta, ctypes.byref(v))
+    U.backend.call("gfb_hamiltonian_general", U._h, p._h, driver.c_plaq, driver.c_rect, ctypes.byref(v))
     return v.value
 
 
@@ -578,22 +653,55 @@ def update_gaugefields_(U, P, step_size, driver=None):
     return U
 
 
-def update_momenta_(P, U, step_size, driver):
-    """update_momenta!(P, U, step_size, driver) (src/molecular_dynamics.jl:539-551)."""
+def update_momenta_(P, U, step_size, driver, group=None):
+    """update_momenta!(P, U, step_size, driver[, group]) (src/molecular_dynamics.jl:539-583): with an MDForceGroup only the
+    named members of the driver's MDActionSet kick (the elementary kick of SextonWeingarten)."""
     if not math.isfinite(step_size):
         raise ValueError("the momentum step size must be finite; got %s" % step_size)
-    U.backend.call("gfb_update_momenta", P._h, U._h, float(step_size), driver.beta)
+    if group is not None:
+        if not isinstance(driver.action, MDActionSet):
+            raise ValueError("a force group selects members of an MDActionSet")
+        cp, cr = driver.action.coefficients(_force_group(group).names)
+    else:
+        cp, cr = driver.c_plaq, driver.c_rect
+    U.backend.call("gfb_update_momenta_general", P._h, U._h, float(step_size), cp, cr)
     return P
 
 
-def md_force_(force, action, U, workspace=None):
-    """md_force!(force, action::GaugeAction, U, workspace) (src/molecular_dynamics.jl:251-267)."""
-    U.backend.call("gfb_force", force._h, U._h, action.wilson_beta())
+def md_force_(force, action, U, workspace=None, group=None):
+    """md_force!(force, action, U, workspace[, group]) (src/molecular_dynamics.jl:251-267, 205-236)."""
+    if group is not None:
+        cp, cr = action.coefficients(_force_group(group).names)
+    else:
+        cp, cr = action.coefficients()
+    U.backend.call("gfb_force_general", force._h, U._h, cp, cr)
     return None
 
 
+def _fast_qpq(U, P, duration, nsteps, driver, fast):
+    """_md_fast_qpq! (src/molecular_dynamics.jl:618-635)."""
+    eps = duration / nsteps
+    update_gaugefields_(U, P, eps / 2, driver)
+    for k in range(nsteps):
+        update_momenta_(P, U, eps, driver, fast)
+        update_gaugefields_(U, P, eps / 2 if k == nsteps - 1 else eps, driver)
+
+
 def md_step_(integrator, U, P, step_size, driver):
-    """md_step! for PQP / QPQ (src/molecular_dynamics.jl:604-616)."""
+    """md_step! for PQP / QPQ / SextonWeingarten / a callable (src/molecular_dynamics.jl:585-700)."""
+    if isinstance(integrator, SextonWeingarten):
+        sw = integrator
+        if sw.ordering is QPQ:
+            _fast_qpq(U, P, step_size / 2, sw.n_fast, driver, sw.fast)
+            update_momenta_(P, U, step_size, driver, sw.slow)
+            _fast_qpq(U, P, step_size / 2, sw.n_fast, driver, sw.fast)
+        else:
+            update_momenta_(P, U, step_size / 2, driver, sw.slow)
+            _fast_qpq(U, P, step_size, sw.n_fast, driver, sw.fast)
+            update_momenta_(P, U, step_size / 2, driver, sw.slow)
+        return None
+    if callable(integrator) and not isinstance(integrator, type):
+        return integrator(U, P, step_size, driver)
     integ = integrator if isinstance(integrator, type) else type(integrator)
     if integ is PQP:
         update_momenta_(P, U, step_size / 2, driver)
@@ -620,17 +728,27 @@ class TrajectoryResult(tuple):
 
 
 def md_trajectory_(U, P, driver, diagnostics=True):
-    """md_trajectory!(U, p, driver; diagnostics=true) (src/molecular_dynamics.jl:712-730)."""
+    """md_trajectory!(U, p, driver; diagnostics=true) (src/molecular_dynamics.jl:712-730).  QPQ / PQP trajectories are ONE
+    library call (fused kick+drift kernels); a SextonWeingarten or callable integrator runs the reference's host loop over
+    md_step!, each elementary kick / drift one kernel."""
     if U.lattice != P.lattice:
         raise ValueError("U and P must have the same number of directions / lattice")
-    H = (ctypes.c_double * 2)() if diagnostics else None
-    U.backend.call(
-        "gfb_md_trajectory", U._h, P._h, driver.beta, driver.steps, driver.trajectory_length, driver.integrator.code,
-        1 if driver.fused else 0, H,
-    )
+    if driver.integrator in (QPQ, PQP):
+        H = (ctypes.c_double * 2)() if diagnostics else None
+        U.backend.call(
+            "gfb_md_trajectory_general", U._h, P._h, driver.c_plaq, driver.c_rect, driver.steps, driver.trajectory_length,
+            driver.integrator.code, 1 if driver.fused else 0, H,
+        )
+        if not diagnostics:
+            return None
+        return TrajectoryResult(H[0], H[1])
+    h0 = md_hamiltonian(U, P, driver) if diagnostics else None
+    eps = md_step_size(driver)
+    for _ in range(driver.steps):
+        md_step_(driver.integrator, U, P, eps, driver)
     if not diagnostics:
         return None
-    return TrajectoryResult(H[0], H[1])
+    return TrajectoryResult(h0, md_hamiltonian(U, P, driver))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -652,10 +770,53 @@ def gradient_flow(U, steps=1, step_size=0.01):
     return Gradientflow(U, Nflow=steps, eps=step_size)
 
 
+class Gradientflow_general:
+    """Gradientflow_general(U, linknames, linkvalues; Nflow=1, eps=0.01) (src/smearing/gradientflow.jl:33-116): RK3 flow of
+    the action sum_i linkvalues[i] * (loops_i + loops_i'), loops by name ("plaquette", "rectangular"), real values."""
+
+    def __init__(self, U, linknames, linkvalues, Nflow=1, eps=0.01):
+        if len(linknames) != len(linkvalues):
+            raise ValueError("linknames and linkvalues must have the same length")
+        action = GaugeAction(U)
+        for name, value in zip(linknames, linkvalues):
+            loops = make_loops_fromname(str(name).lstrip(":"))
+            action.push(value, loops + loops.adjoint())
+        self.c_plaq, self.c_rect = action.coefficients()
+        self.Nflow, self.eps = int(Nflow), float(eps)
+
+
 def flow_(U, g):
-    """flow!(U, g::Gradientflow) (src/smearing/gradientflow.jl:171-238): g.Nflow RK3 steps."""
-    U.backend.call("gfb_flow", U._h, g.eps, g.Nflow)
+    """flow!(U, g::Gradientflow | Gradientflow_general) (src/smearing/gradientflow.jl:171-316): g.Nflow RK3 steps."""
+    if isinstance(g, Gradientflow_general):
+        U.backend.call("gfb_flow_general", U._h, g.eps, g.Nflow, g.c_plaq, g.c_rect)
+    else:
+        U.backend.call("gfb_flow", U._h, g.eps, g.Nflow)
     return U
+
+
+_TOPO = {"plaquette": 0, "clover": 1, "improved": 2}
+
+
+def topological_charge(U, method="plaquette"):
+    """topological_charge(U; method=:plaquette | :clover | :improved) (src/AbstractGaugefields.jl:1471-1490)."""
+    m = str(method).lstrip(":")
+    if m not in _TOPO:
+        raise ValueError("supported topological_charge methods are :plaquette, :clover, and :improved")
+    v = ctypes.c_double()
+    U.backend.call("gfb_topological_charge", U._h, _TOPO[m], ctypes.byref(v))
+    return v.value
+
+
+def topological_charge_density(U, method="plaquette"):
+    """topological_charge_density(U; method) (src/AbstractGaugefields.jl:1447-1461): q(x) as an array indexed [t, z, y, x]
+    (the reference's density[ix, iy, iz, it] in column-major order)."""
+    m = str(method).lstrip(":")
+    if m not in _TOPO:
+        raise ValueError("supported topological_charge_density methods are :plaquette, :clover, and :improved")
+    nx, ny, nz, nt = U.lattice
+    out = np.zeros((nt, nz, ny, nx), dtype=np.float64)
+    U.backend.call("gfb_topological_charge_density", U._h, _TOPO[m], out.ctypes.data_as(ctypes.c_void_p))
+    return out
 
 
 class StoutSmearing:

@@ -147,6 +147,32 @@ int gfb_kick_from_dSdU(gfb_mom* p, gfb_gauge* u, gfb_gauge* dsdu, double factor)
 /* calc_dSdUmu! for the Wilson action at coefficient beta/2 (GaugeActions.jl:95-123): d = (beta/2) * sum of 6 staples */
 int gfb_wilson_dSdU(gfb_gauge* d, gfb_gauge* g, double beta);
 
+/* ---- general-action path: plaquette + rectangle terms (Symanzik / Iwasaki / DBW2 type actions) ----------------------------
+ * A GaugeAction with the terms (c_plaq, plaquette + plaquette') and (c_rect, rectangular + rectangular')
+ * (GaugeAction/push!, src/action/GaugeActions.jl:23-62; "rectangular" = the 1x2 and 2x1 loops of every plane,
+ * src/autostaples/wilsonloops.jl:233-245).  dSdU_mu = c_plaq * (6 plaquette staples) + c_rect * (18 rectangle staples)
+ * (calc_dSdUmu!, GaugeActions.jl:95-123).  c_rect = 0 runs the Wilson kernels; c_rect != 0 needs a single-GPU context
+ * (GFB_ERR_ARG otherwise: the t-slab halo is one slice wide). */
+/* out2 = { sum_{x, mu<nu} Re tr P_munu, sum_x Re tr of the 12 rectangle loops }: evaluate_GaugeAction's building blocks
+ * (GaugeActions.jl:132-142); Re evaluate_GaugeAction = 2 * (c_plaq * out2[0] + c_rect * out2[1]) */
+int gfb_loop_sums(gfb_gauge* g, double* out2);
+/* md_force!(F, action, U, ws) (molecular_dynamics.jl:251-267): F_mu = -(1/NC) TAcoeffs(U_mu dSdU_mu) */
+int gfb_force_general(gfb_mom* f, gfb_gauge* g, double c_plaq, double c_rect);
+/* update_momenta!(P, U, eps, driver) for that action (molecular_dynamics.jl:539-551) */
+int gfb_update_momenta_general(gfb_mom* p, gfb_gauge* g, double eps, double c_plaq, double c_rect);
+/* md_hamiltonian = -(1/NC) Re evaluate_GaugeAction + p*p/2 (molecular_dynamics.jl:494-505, 247-249) */
+int gfb_hamiltonian_general(gfb_gauge* g, gfb_mom* p, double c_plaq, double c_rect, double* out);
+/* md_trajectory! for that action; arguments as gfb_md_trajectory */
+int gfb_md_trajectory_general(gfb_gauge* g, gfb_mom* p, double c_plaq, double c_rect, int steps, double tau, int integrator, int fused, double* H);
+/* flow!(U, ::Gradientflow_general) (src/smearing/gradientflow.jl:240-316) with link values (c_plaq, c_rect) for the loop sets
+ * ("plaquette", "rectangular"); (1, 0) is gfb_flow */
+int gfb_flow_general(gfb_gauge* g, double eps, int nsteps, double c_plaq, double c_rect);
+/* topological_charge(U; method) / topological_charge_density(U; method) (src/AbstractGaugefields.jl:1447-1490):
+ * method 0 :plaquette, 1 :clover, 2 :improved (needs a single-GPU context).  host_density = Float64[NX,NY,NZ,NT]. */
+enum gfb_topo_method { GFB_Q_PLAQUETTE = 0, GFB_Q_CLOVER = 1, GFB_Q_IMPROVED = 2 };
+int gfb_topological_charge(gfb_gauge* g, int method, double* out);
+int gfb_topological_charge_density(gfb_gauge* g, int method, double* host_density);
+
 /* ---- primitive table ---------------------------------------------------------------------------
  * The element-wise operations that Gaugefields.jl's generic (un-fused) algorithms are written in; each forwards to one
  * LatticeMatrices kernel in the reference (src/4D/mpi_jacc/gaugefields_4D_MPILattice.jl:474-842,
