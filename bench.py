@@ -167,7 +167,7 @@ def _oracle_step(oracle, workload, dims, beta, eps):
     P = oracle.gaussian_momenta(dims, 0x5678, 0)
     if workload == "stout48":
         def step():
-            oracle.update_links(U, P, dims, eps / 2)
+            U[...] = oracle.update_links(U, P, dims, eps / 2)
             tape, cur = [], U
             for _ in range(STOUT_LAYERS):
                 tape.append(cur)
@@ -176,7 +176,7 @@ def _oracle_step(oracle, workload, dims, beta, eps):
             for inp in reversed(tape):
                 d = oracle.stout_backward(d, inp, dims, STOUT_RHO)
             oracle.kick_from_dSdU(P, U, d, dims, -eps / 3.0)
-            oracle.update_links(U, P, dims, eps / 2)
+            U[...] = oracle.update_links(U, P, dims, eps / 2)
         return step
     return lambda: oracle.md_step(U, P, dims, beta, eps, 0)
 

@@ -806,3 +806,169 @@ void orc_staple_sum(double* V, const double* U, const int* dims) {
 }
 
 }  // extern "C"
+
+// ================================================================================================
+// General-action path: plaquette + rectangle terms, loop sums, topological charge.
+// Restates the GENERIC machinery of the reference (not the hand-derived staples the CUDA kernels use): an action term is a
+// coefficient times a set of closed loops plus their adjoints (GaugeAction/push!, src/action/GaugeActions.jl:23-62;
+// Gradientflow_general appends loop' itself, src/smearing/gradientflow.jl:88-101); dS/dU_mu is obtained by deleting U_mu
+// from every loop that contains it (make_staple in Wilsonloop.jl; calc_dSdUmu!, GaugeActions.jl:95-123), so
+// U_mu(x) dSdU_mu(x) = sum over loops W in (set + adjoint set) and over the +mu steps k of W of the loop re-started at that
+// step and evaluated with the step at x.
+// ================================================================================================
+namespace {
+
+typedef std::vector<Step> Loop;
+
+// "plaquette": (mu,1)(nu,1)(mu,-1)(nu,-1) for mu < nu;  "rectangular": (mu,1)(nu,2)(mu,-1)(nu,-2) and (mu,2)(nu,1)(mu,-2)(nu,-1)
+// (src/autostaples/wilsonloops.jl:219-245)
+std::vector<Loop> loop_set(int kind) {
+    std::vector<Loop> out;
+    auto seg = [](Loop& l, int mu, int n) { for (int k = 0; k < std::abs(n); k++) l.push_back(Step{mu, n > 0 ? 1 : -1}); };
+    for (int mu = 0; mu < 4; mu++)
+        for (int nu = mu + 1; nu < 4; nu++) {
+            if (kind == 0) {
+                Loop l; seg(l, mu, 1); seg(l, nu, 1); seg(l, mu, -1); seg(l, nu, -1); out.push_back(l);
+            } else {
+                Loop a; seg(a, mu, 1); seg(a, nu, 2); seg(a, mu, -1); seg(a, nu, -2); out.push_back(a);
+                Loop b; seg(b, mu, 2); seg(b, nu, 1); seg(b, mu, -2); seg(b, nu, -1); out.push_back(b);
+            }
+        }
+    return out;
+}
+// adjoint loop: reversed path with reversed steps (Wilsonline adjoint)
+Loop adjoint_loop(const Loop& l) {
+    Loop r;
+    for (int k = (int)l.size() - 1; k >= 0; k--) r.push_back(Step{l[k].mu, -l[k].sgn});
+    return r;
+}
+// all loops of (set + adjoints) re-started at each of their +mu steps: closed paths that begin with U_mu(x)
+std::vector<Loop> rotations_through(int kind, int mu) {
+    std::vector<Loop> out;
+    std::vector<Loop> all = loop_set(kind);
+    const size_t n0 = all.size();
+    for (size_t i = 0; i < n0; i++) all.push_back(adjoint_loop(all[i]));
+    for (const Loop& l : all)
+        for (size_t k = 0; k < l.size(); k++)
+            if (l[k].mu == mu && l[k].sgn > 0) {
+                Loop r;
+                for (size_t j = 0; j < l.size(); j++) r.push_back(l[(k + j) % l.size()]);
+                out.push_back(r);
+            }
+    return out;
+}
+
+M3 U_dSdU_general(const double* U, const Lat& L, const int* x, const std::vector<Loop>& plaq, const std::vector<Loop>& rect, double c_plaq, double c_rect) {
+    M3 acc = zero3();
+    if (c_plaq != 0.0) for (const Loop& l : plaq) acc = add(acc, scale(c_plaq, path_product(U, L, x, l.data(), (int)l.size())));
+    if (c_rect != 0.0) for (const Loop& l : rect) acc = add(acc, scale(c_rect, path_product(U, L, x, l.data(), (int)l.size())));
+    return acc;
+}
+
+int eps4(int a, int b, int c, int d) {
+    int p[4] = {a, b, c, d};
+    for (int i = 0; i < 4; i++) for (int j = i + 1; j < 4; j++) if (p[i] == p[j]) return 0;
+    int inv = 0;
+    for (int i = 0; i < 4; i++) for (int j = i + 1; j < 4; j++) inv += p[i] > p[j];
+    return (inv % 2 == 0) ? 1 : -1;
+}
+
+}  // namespace
+
+extern "C" {
+
+// scale = -1/3: md_force! (molecular_dynamics.jl:251-267);  scale = 1: F_update! of the general flow (gradientflow.jl:318-334)
+void orc_force_general(double* F, const double* U, const int* dims, double c_plaq, double c_rect, double scale_) {
+    Lat L(dims);
+    std::vector<Loop> plaq[4], rect[4];
+    for (int mu = 0; mu < 4; mu++) { plaq[mu] = rotations_through(0, mu); rect[mu] = rotations_through(1, mu); }
+#pragma omp parallel for
+    for (long s = 0; s < L.V; s++) {
+        int x[4];
+        L.coord(s, x);
+        for (int mu = 0; mu < 4; mu++) {
+            double c[8];
+            ta_coeffs(U_dSdU_general(U, L, x, plaq[mu], rect[mu], c_plaq, c_rect), c);
+            double* f = F + ((long)mu * L.V + s) * 8;
+            for (int a = 0; a < 8; a++) f[a] = scale_ * c[a];
+        }
+    }
+}
+// number of loop rotations through a link: 6 for the plaquette set, 18 for the rectangular set (sanity probe for the tests)
+int orc_rotations_through(int kind, int mu) { return (int)rotations_through(kind, mu).size(); }
+
+// out2 = { sum_x sum_{plaquette loops} Re tr, sum_x sum_{rectangular loops} Re tr } (loops without their adjoints)
+void orc_loop_sums(const double* U, const int* dims, double* out2) {
+    Lat L(dims);
+    const std::vector<Loop> plaq = loop_set(0), rect = loop_set(1);
+    double sp = 0.0, sr = 0.0;
+#pragma omp parallel for reduction(+ : sp, sr)
+    for (long s = 0; s < L.V; s++) {
+        int x[4];
+        L.coord(s, x);
+        for (const Loop& l : plaq) sp += trace(path_product(U, L, x, l.data(), (int)l.size())).real();
+        for (const Loop& l : rect) sr += trace(path_product(U, L, x, l.data(), (int)l.size())).real();
+    }
+    out2[0] = sp; out2[1] = sr;
+}
+
+// topological_charge_density(U; method) (src/AbstractGaugefields.jl:1184-1400): method 0 plaquette, 1 clover, 2 improved.
+// q(x) = -Re sum_{mu nu rho sigma} eps tr(F_munu F_rhosigma) / (32 pi^2 n^2) with F = TA(sum of the method's loops)
+void orc_topological_charge_density(const double* U, const int* dims, int method, double* out) {
+    Lat L(dims);
+    auto field_loops = [](int kind, int mu, int nu) {
+        std::vector<Loop> ls;
+        auto mk = [&](std::initializer_list<std::pair<int, int>> segs) {
+            Loop l;
+            for (auto sg : segs) for (int k = 0; k < std::abs(sg.second); k++) l.push_back(Step{sg.first, sg.second > 0 ? 1 : -1});
+            ls.push_back(l);
+        };
+        if (kind == 0) {
+            mk({{mu, 1}, {nu, 1}, {mu, -1}, {nu, -1}});
+        } else if (kind == 1) {  // make_cloverloops, src/autostaples/wilsonloops.jl:166-177
+            mk({{mu, 1}, {nu, 1}, {mu, -1}, {nu, -1}});
+            mk({{nu, 1}, {mu, -1}, {nu, -1}, {mu, 1}});
+            mk({{nu, -1}, {mu, 1}, {nu, 1}, {mu, -1}});
+            mk({{mu, -1}, {nu, -1}, {mu, 1}, {nu, 1}});
+        } else {  // _rectangle_loops, src/AbstractGaugefields.jl:1316-1330
+            mk({{mu, 2}, {nu, 1}, {mu, -2}, {nu, -1}});
+            mk({{nu, 1}, {mu, -2}, {nu, -1}, {mu, 2}});
+            mk({{nu, -1}, {mu, 2}, {nu, 1}, {mu, -2}});
+            mk({{mu, -2}, {nu, -1}, {mu, 2}, {nu, 1}});
+            mk({{mu, 1}, {nu, 2}, {mu, -1}, {nu, -2}});
+            mk({{nu, 2}, {mu, -1}, {nu, -2}, {mu, 1}});
+            mk({{nu, -2}, {mu, 1}, {nu, 2}, {mu, -1}});
+            mk({{mu, -1}, {nu, -2}, {mu, 1}, {nu, 2}});
+        }
+        return ls;
+    };
+    auto density = [&](int kind, double weight, bool accumulate) {
+        const double nl = kind == 0 ? 1.0 : (kind == 1 ? 4.0 : 8.0), rect_factor = kind == 2 ? 2.0 : 1.0;
+        std::vector<Loop> loops[4][4];
+        for (int mu = 0; mu < 4; mu++) for (int nu = 0; nu < 4; nu++) if (mu != nu) loops[mu][nu] = field_loops(kind, mu, nu);
+#pragma omp parallel for
+        for (long s = 0; s < L.V; s++) {
+            int x[4];
+            L.coord(s, x);
+            M3 Fs[4][4];
+            for (int mu = 0; mu < 4; mu++)
+                for (int nu = 0; nu < 4; nu++) {
+                    if (mu == nu) continue;
+                    M3 w = zero3();
+                    for (const Loop& l : loops[mu][nu]) w = add(w, path_product(U, L, x, l.data(), (int)l.size()));
+                    Fs[mu][nu] = ta_matrix(w);
+                }
+            cd q = 0.0;
+            for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) for (int c = 0; c < 4; c++) for (int d = 0; d < 4; d++) {
+                const int e = eps4(a, b, c, d);
+                if (e != 0) q += (double)e * trace(mul(Fs[a][b], Fs[c][d]));
+            }
+            const double v = weight * (-rect_factor * q.real() / (32.0 * M_PI * M_PI * nl * nl));
+            out[s] = accumulate ? out[s] + v : v;
+        }
+    };
+    if (method == 2) { density(1, 5.0 / 3.0, false); density(2, -1.0 / 12.0, true); }
+    else density(method, 1.0, false);
+}
+
+}  // extern "C"

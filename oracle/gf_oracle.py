@@ -233,3 +233,92 @@ def exp_pullback(C, Q, route=0):
     lib().orc_exp_pullback.restype = ctypes.c_int
     ok = lib().orc_exp_pullback(_dp(c), _dp(q), ctypes.c_int(route), _dp(out))
     return out.T.copy(), bool(ok)
+
+
+# ---- general-action path (plaquette + rectangle terms), loop sums, topological charge ------------------------------------
+def force_general(U, dims, c_plaq, c_rect, scale=-1.0 / 3.0):
+    """md_force! of the action c_plaq (plaq + plaq') + c_rect (rect + rect') by generic loop differentiation; scale = 1 gives
+    F_update! of Gradientflow_general."""
+    F = new_p(dims)
+    lib().orc_force_general(_dp(F), _dp(U), _dims(dims), ctypes.c_double(c_plaq), ctypes.c_double(c_rect), ctypes.c_double(scale))
+    return F
+
+
+def loop_sums(U, dims):
+    out = np.zeros(2)
+    lib().orc_loop_sums(_dp(U), _dims(dims), _dp(out))
+    return out[0], out[1]
+
+
+def hamiltonian_general(U, P, dims, c_plaq, c_rect):
+    sp, sr = loop_sums(U, dims)
+    return -(2.0 / 3.0) * (c_plaq * sp + c_rect * sr) + 0.5 * momentum_norm2(P, dims)
+
+
+def update_momenta_general(P, U, dims, eps, c_plaq, c_rect):
+    P += eps * force_general(U, dims, c_plaq, c_rect)
+    return P
+
+
+def md_trajectory_general(U, P, dims, c_plaq, c_rect, steps, tau=1.0, integrator=0):
+    """md_trajectory! with md_step! QPQ (0) / PQP (1) for the general action; U, P updated in place; returns (H0, H1)."""
+    H0 = hamiltonian_general(U, P, dims, c_plaq, c_rect)
+    eps = tau / steps
+    for _ in range(steps):
+        if integrator == 0:
+            U[...] = update_links(U, P, dims, eps / 2)
+            update_momenta_general(P, U, dims, eps, c_plaq, c_rect)
+            U[...] = update_links(U, P, dims, eps / 2)
+        else:
+            update_momenta_general(P, U, dims, eps / 2, c_plaq, c_rect)
+            U[...] = update_links(U, P, dims, eps)
+            update_momenta_general(P, U, dims, eps / 2, c_plaq, c_rect)
+    return H0, hamiltonian_general(U, P, dims, c_plaq, c_rect)
+
+
+def flow_step_general(U, dims, eps, c_plaq, c_rect):
+    """One RK3 step of flow!(U, ::Gradientflow_general) (src/smearing/gradientflow.jl:240-316), in place."""
+    F0 = force_general(U, dims, c_plaq, c_rect, 1.0)
+    W1 = update_links(U, -eps / 4 * F0, dims, 1.0)
+    F1 = force_general(W1, dims, c_plaq, c_rect, 1.0)
+    W2 = update_links(W1, -(8 * eps / 9) * F1 + (17 * eps / 36) * F0, dims, 1.0)
+    F2 = force_general(W2, dims, c_plaq, c_rect, 1.0)
+    U[...] = update_links(W2, -(3 * eps / 4) * F2 + (8 * eps / 9) * F1 - (17 * eps / 36) * F0, dims, 1.0)
+    return U
+
+
+def topological_charge_density(U, dims, method):
+    """method 0 plaquette, 1 clover, 2 improved; array indexed [t, z, y, x]."""
+    nx, ny, nz, nt = dims
+    out = np.zeros((nt, nz, ny, nx))
+    lib().orc_topological_charge_density(_dp(U), _dims(dims), ctypes.c_int(method), _dp(out))
+    return out
+
+
+def sexton_weingarten_trajectory(U, P, dims, terms, fast, slow, n_fast, steps, tau, ordering=0):
+    """md_trajectory! with the SextonWeingarten integrator (src/molecular_dynamics.jl:618-700): `terms` maps a name to
+    (c_plaq, c_rect); fast / slow are tuples of names.  In place; returns (H0, H1) of the full action."""
+    def coeff(names):
+        return sum(terms[n][0] for n in names), sum(terms[n][1] for n in names)
+
+    cf, cs, ca = coeff(fast), coeff(slow), coeff(tuple(terms))
+
+    def fast_qpq(duration):
+        e = duration / n_fast
+        U[...] = update_links(U, P, dims, e / 2)
+        for k in range(n_fast):
+            update_momenta_general(P, U, dims, e, *cf)
+            U[...] = update_links(U, P, dims, e / 2 if k == n_fast - 1 else e)
+
+    H0 = hamiltonian_general(U, P, dims, *ca)
+    eps = tau / steps
+    for _ in range(steps):
+        if ordering == 0:
+            fast_qpq(eps / 2)
+            update_momenta_general(P, U, dims, eps, *cs)
+            fast_qpq(eps / 2)
+        else:
+            update_momenta_general(P, U, dims, eps / 2, *cs)
+            fast_qpq(eps)
+            update_momenta_general(P, U, dims, eps / 2, *cs)
+    return H0, hamiltonian_general(U, P, dims, *ca)
