@@ -792,6 +792,26 @@ int gfb_mom_axpy(gfb_mom* p, double t, const gfb_mom* f) {
     return GFB_OK;
 }
 
+// add_U!(P[mu], t, F[mu]) on ONE direction (the loop body of update_momenta!, molecular_dynamics.jl:580-582): the momenta of a
+// direction are the 8 coefficient planes [mu*8, mu*8+8) of every time-slice
+int gfb_mom_axpy_dir(gfb_mom* p, int mu, double t, const gfb_mom* f) {
+    if (!p || !f) return fail(p ? p->ctx : nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = p->ctx;
+    if (!same_shape(p, f)) return fail(ctx, GFB_ERR_ARG, "momentum fields differ in shape");
+    if (mu < 0 || mu > 3) return fail(ctx, GFB_ERR_ARG, "mu must be in 0..3");
+    if (!std::isfinite(t)) return fail(ctx, GFB_ERR_ARG, "the step size must be finite");
+    const size_t v3 = (size_t)p->nx * p->ny * p->nz;
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
+        for (int tt = 0; tt < p->tloc; tt++) {
+            const size_t off = ((size_t)tt * 32 + (size_t)mu * 8) * v3;
+            launch_axpy(ctx->slabs[i].stream, p->d[i] + off, t, f->d[i] + off, 8 * v3);
+        }
+        GFB_CHECK(post_launch(ctx, p->tloc));
+    }
+    return GFB_OK;
+}
+
 // ---- initial fields -----------------------------------------------------------------------------
 int gfb_set_cold(gfb_gauge* g) {
     if (!g) return fail(nullptr, GFB_ERR_ARG, "null argument");

@@ -43,6 +43,7 @@ SIGNATURES = {
     "gfb_mom_copy": (c_int, [c_void_p, c_void_p]),
     "gfb_mom_zero": (c_int, [c_void_p]),
     "gfb_mom_axpy": (c_int, [c_void_p, c_double, c_void_p]),
+    "gfb_mom_axpy_dir": (c_int, [c_void_p, c_int, c_double, c_void_p]),
     "gfb_set_cold": (c_int, [c_void_p]),
     "gfb_set_hot": (c_int, [c_void_p, c_u64, c_int]),
     "gfb_gaussian_momenta": (c_int, [c_void_p, c_u64, c_u64, c_double, c_int]),

@@ -337,9 +337,13 @@ class Momenta:
         self.backend.call("gfb_mom_zero", self._h)
         return self
 
-    def add_(self, t, other):
-        """add_U!(P, t, F) (TA_gaugefields_4D_serial.jl:150-173)."""
-        self.backend.call("gfb_mom_axpy", self._h, float(t), other._h)
+    def add_(self, t, other, mu=None):
+        """add_U!(P, t, F) on all four directions, or add_U!(P[mu], t, F[mu]) (TA_gaugefields_4D_serial.jl:150-173): how an
+        external force provider (md_force! of a fermion action, say) adds into the momenta of this backend."""
+        if mu is None:
+            self.backend.call("gfb_mom_axpy", self._h, float(t), other._h)
+        else:
+            self.backend.call("gfb_mom_axpy_dir", self._h, int(mu), float(t), other._h)
         return self
 
 

@@ -94,6 +94,8 @@ int gfb_mom_copy(gfb_mom* dst, const gfb_mom* src);
 int gfb_mom_zero(gfb_mom* p); /* clear_U! on momenta, TA_gaugefields_4D_MPILattice.jl:285-291 */
 /* add_U!(P, t, F) on momenta (TA_gaugefields_4D_serial.jl:150-173) */
 int gfb_mom_axpy(gfb_mom* p, double t, const gfb_mom* f);
+/* the same on one direction: add_U!(P[mu], t, F[mu]) (molecular_dynamics.jl:580-582) */
+int gfb_mom_axpy_dir(gfb_mom* p, int mu, double t, const gfb_mom* f);
 
 /* ---- initial fields and random numbers ------------------------------------------------------ */
 int gfb_set_cold(gfb_gauge* g);                              /* IdentityGauges, AbstractGaugefields.jl:431-548 */
