@@ -49,7 +49,7 @@ def header_signatures():
             return "pptr"
         if stars == 1:
             return "ptr"
-        return {"int": "int", "double": "double", "uint64_t": "u64", "size_t": "size", "long long": "i64", "void": "void"}[base]
+        return {"int": "int", "double": "double", "uint64_t": "u64", "size_t": "u64", "long long": "i64", "void": "void"}[base]
 
     out = {}
     for ret, name, args in re.findall(r"^\s*((?:const\s+)?[A-Za-z_][A-Za-z0-9_ ]*?\s*\*?)\s*(gfb_[a-zA-Z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.M):
@@ -76,8 +76,8 @@ def test_ctypes_argument_types_match_header():
             return "double"
         if t is ctypes.c_uint64:
             return "u64"
-        if t is ctypes.c_size_t:
-            return "size"
+        if t is ctypes.c_size_t:  # the same ctypes object as c_uint64 on LP64: one class for both
+            return "u64"
         if t is ctypes.c_longlong:
             return "i64"
         if t is ctypes.c_char_p:
@@ -134,7 +134,7 @@ def julia_ccalls():
 
 
 def test_julia_ccalls_match_header():
-    JL = {"Cint": "int", "Cdouble": "double", "UInt64": "u64", "Csize_t": "size", "Clonglong": "i64", "Cstring": "str",
+    JL = {"Cint": "int", "Cdouble": "double", "UInt64": "u64", "Csize_t": "u64", "Clonglong": "i64", "Cstring": "str",
           "Ptr{Cvoid}": "ptr", "Ptr{Cdouble}": "ptr", "Ref{Cdouble}": "ptr", "Ptr{ComplexF64}": "ptr", "Ptr{Cint}": "ptr",
           "Ptr{UInt8}": "ptr", "Ref{Ptr{Cvoid}}": "pptr"}
     hdr = header_signatures()
