@@ -376,6 +376,8 @@ static void release_gauge_memory(gfb_gauge* g) {
     gfb_ctx* ctx = g->ctx;
     if (!ctx) return;
     release_like(ctx, g->alt);
+    for (size_t i = 0; i < g->wide.size(); i++) { cudaSetDevice(ctx->slabs[i].device); cudaFree(g->wide[i]); }
+    g->wide.clear();
     for (size_t i = 0; i < g->z.size(); i++) { cudaSetDevice(ctx->slabs[i].device); cudaFree(g->z[i]); }
     g->z.clear();
     release_like(ctx, g->d);
@@ -393,6 +395,8 @@ static int post_launch(gfb_ctx* ctx, int nlaunch = 1) {
 }
 
 extern "C" {
+
+static int build_wide(gfb_gauge* g, const std::vector<double2*>& src, Geom* wide_geom);
 
 int gfb_version(void) { return 100; }
 
@@ -923,16 +927,19 @@ int gfb_hamiltonian(gfb_gauge* g, gfb_mom* p, double beta, double* out) {
 int gfb_loop_sums(gfb_gauge* g, double* out2) {
     if (!g || !out2) return fail(g ? g->ctx : nullptr, GFB_ERR_ARG, "null argument");
     gfb_ctx* ctx = g->ctx;
-    if (ctx->nslabs_total > 1) return fail(ctx, GFB_ERR_ARG, "rectangle loops need a halo of width 2: use a single-GPU context");
-    Slab& s = ctx->slabs[0];
-    Geom geo = geom_of(g, 0);
-    GFB_CHECK(ensure_partial(ctx, s, (size_t)plaquette_blocks(geo) * 2 + 16));
-    GFB_CUDA(ctx, cudaSetDevice(s.device));
-    int nb = 0;
-    launch_loop_sums(s.stream, geo, g->d[0], s.d_partial, &nb);
-    launch_final_reduce(s.stream, s.d_partial, nb, s.d_result);
-    launch_final_reduce(s.stream, s.d_partial + nb, nb, s.d_result + 1);
-    GFB_CHECK(post_launch(ctx, 3));
+    Geom gw = geom_of(g, 0);
+    const bool wide = ctx->nslabs_total > 1;
+    if (wide) GFB_CHECK(build_wide(g, g->d, &gw));
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        Slab& s = ctx->slabs[i];
+        GFB_CHECK(ensure_partial(ctx, s, (size_t)plaquette_blocks(geom_of(g, i)) * 2 + 16));
+        GFB_CUDA(ctx, cudaSetDevice(s.device));
+        int nb = 0;
+        launch_loop_sums(s.stream, gw, wide ? 2 : 0, g->tloc, wide ? g->wide[i] : g->d[i], s.d_partial, &nb);
+        launch_final_reduce(s.stream, s.d_partial, nb, s.d_result);
+        launch_final_reduce(s.stream, s.d_partial + nb, nb, s.d_result + 1);
+        GFB_CHECK(post_launch(ctx, 3));
+    }
     return gather_scalars(ctx, 2, out2);
 }
 
@@ -941,22 +948,26 @@ int gfb_loop_sums(gfb_gauge* g, double* out2) {
 static int topological_density(gfb_gauge* g, int method, std::vector<double*>& dens) {
     gfb_ctx* ctx = g->ctx;
     if (method < 0 || method > 2) return fail(ctx, GFB_ERR_ARG, "supported topological charge methods are plaquette (0), clover (1) and improved (2)");
-    if (method == 2 && ctx->nslabs_total > 1) return fail(ctx, GFB_ERR_ARG, "the improved topological charge uses rectangle loops (halo of width 2): use a single-GPU context");
-    GFB_CHECK(ensure_halo(g));
+    // the clover leaves reach one site back and forward in two directions, the rectangle loops two sites: on t-slabs all three
+    // methods read the wide copy of the slab
+    Geom gw = geom_of(g, 0);
+    const bool wide = ctx->nslabs_total > 1;
+    if (wide) GFB_CHECK(build_wide(g, g->d, &gw));
+    const int tb = wide ? 2 : 0;
     dens.assign(ctx->slabs.size(), nullptr);
     for (size_t i = 0; i < ctx->slabs.size(); i++) {
         Slab& s = ctx->slabs[i];
-        Geom geo = geom_of(g, i);
-        const size_t n = (size_t)geo.v3 * geo.tloc;
+        const size_t n = (size_t)gw.v3 * g->tloc;
         GFB_CHECK(ensure_staging(ctx, s, n * sizeof(double)));
         GFB_CUDA(ctx, cudaSetDevice(s.device));
         dens[i] = reinterpret_cast<double*>(s.d_staging);
+        const double2* u = wide ? g->wide[i] : g->d[i];
         if (method == 2) {
-            launch_topological_density(s.stream, geo, g->d[i], dens[i], 1, 5.0 / 3.0, false);
-            launch_topological_density(s.stream, geo, g->d[i], dens[i], 2, -1.0 / 12.0, true);
+            launch_topological_density(s.stream, gw, tb, g->tloc, tb, u, dens[i], 1, 5.0 / 3.0, false);
+            launch_topological_density(s.stream, gw, tb, g->tloc, tb, u, dens[i], 2, -1.0 / 12.0, true);
             GFB_CHECK(post_launch(ctx, 2));
         } else {
-            launch_topological_density(s.stream, geo, g->d[i], dens[i], method, 1.0, false);
+            launch_topological_density(s.stream, gw, tb, g->tloc, tb, u, dens[i], method, 1.0, false);
             GFB_CHECK(post_launch(ctx));
         }
     }
@@ -1095,6 +1106,49 @@ static int links_are_unitary(gfb_gauge* g, bool* yes) {
     return GFB_OK;
 }
 
+// Wide copy of every local slab of `src` for kernels that reach two slices away (rectangle loops): tloc + 4 slices in natural t
+// order -- [0, 2) the previous slab's last two slices, [2, tloc + 2) the slab itself, [tloc + 2, tloc + 4) the next slab's first
+// two -- owned by the configuration handle.  One device copy plus one NCCL send/recv pair per neighbour (two slices each).
+static int build_wide(gfb_gauge* g, const std::vector<double2*>& src, Geom* wide_geom) {
+    gfb_ctx* ctx = g->ctx;
+    const int G = ctx->nslabs_total;
+    if (g->tloc < 2) return fail(ctx, GFB_ERR_ARG, "rectangle terms need at least two time-slices per GPU");
+    const size_t slice = g->slice_elems();  // double2 per slice
+    if (g->wide.empty()) {
+        g->wide.assign(ctx->slabs.size(), nullptr);
+        for (size_t i = 0; i < ctx->slabs.size(); i++) {
+            GFB_CUDA(ctx, cudaSetDevice(ctx->slabs[i].device));
+            GFB_CUDA(ctx, cudaMalloc(&g->wide[i], (size_t)(g->tloc + 4) * slice * sizeof(double2)));
+        }
+    }
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        Slab& s = ctx->slabs[i];
+        GFB_CUDA(ctx, cudaSetDevice(s.device));
+        GFB_CUDA(ctx, cudaMemcpyAsync(g->wide[i] + 2 * slice, src[i], (size_t)g->tloc * slice * sizeof(double2), cudaMemcpyDeviceToDevice, s.stream));
+    }
+    NcclGroup grp;
+    GFB_NCCL(ctx, grp.start());
+    for (size_t i = 0; i < ctx->slabs.size(); i++) {
+        Slab& s = ctx->slabs[i];
+        const int prev = (s.index + G - 1) % G, next = (s.index + 1) % G;
+        const size_t two = 2 * slice * 2;  // doubles in two slices
+        double* own = reinterpret_cast<double*>(src[i]);
+        double* w = reinterpret_cast<double*>(g->wide[i]);
+        GFB_NCCL(ctx, ncclSend(own, two, ncclDouble, prev, s.nccl, s.stream));                                         // my first two -> prev's top halo
+        GFB_NCCL(ctx, ncclSend(own + (size_t)(g->tloc - 2) * slice * 2, two, ncclDouble, next, s.nccl, s.stream));     // my last two -> next's bottom halo
+        GFB_NCCL(ctx, ncclRecv(w + (size_t)(g->tloc + 2) * slice * 2, two, ncclDouble, next, s.nccl, s.stream));
+        GFB_NCCL(ctx, ncclRecv(w, two, ncclDouble, prev, s.nccl, s.stream));
+    }
+    GFB_NCCL(ctx, grp.end());
+    Geom gw = geom_of(g, 0);
+    gw.tloc = g->tloc + 4;
+    gw.nslots = g->tloc + 4;
+    gw.t_up_wrap = 0;            // never taken: the computed slices [2, tloc + 2) reach at most two slices away
+    gw.t_dn_wrap = g->tloc + 3;
+    *wide_geom = gw;
+    return GFB_OK;
+}
+
 // one fused pass over all local slabs: Z' = a*TA(U V^dag) + b*Z ; Uout = exp(c Z') Uin.
 // With several slabs and an output link field, on return (in stream order) uout's halo slots are valid:
 //   peer halos (default): the kernels store their boundary slices into the neighbours' halo slots themselves (NVLink peer
@@ -1105,12 +1159,24 @@ static int fused_pass(gfb_gauge* g, const std::vector<double2*>& uin, const std:
                       const std::vector<double*>* zout, FusedArgs fa) {
     gfb_ctx* ctx = g->ctx;
     if (fa.c_rect != 0.0) {
-        // rectangle staples reach two sites away: the t-slab halo is one slice wide, so this path is single-slab
-        if (ctx->nslabs_total > 1) return fail(ctx, GFB_ERR_ARG, "actions with rectangle terms need a halo of width 2: use a single-GPU context");
-        Slab& s = ctx->slabs[0];
-        GFB_CUDA(ctx, cudaSetDevice(s.device));
-        launch_force_general(s.stream, geom_of(g, 0), uin[0], uout ? (*uout)[0] : nullptr, zin ? (*zin)[0] : nullptr, zout ? (*zout)[0] : nullptr, fa);
-        return post_launch(ctx);
+        // rectangle staples reach two sites away.  One slab: plain periodic addressing.  t-slabs: the one-slice halo slots are
+        // not enough, so the pass runs on a wide copy of the slab (build_wide) and writes into the slab's own slices; the
+        // output's one-slice halo is NOT exchanged here (callers clear halo_valid).
+        if (ctx->nslabs_total == 1) {
+            Slab& s = ctx->slabs[0];
+            GFB_CUDA(ctx, cudaSetDevice(s.device));
+            launch_force_general(s.stream, geom_of(g, 0), 0, g->tloc, 0, uin[0], uout ? (*uout)[0] : nullptr, zin ? (*zin)[0] : nullptr, zout ? (*zout)[0] : nullptr, fa);
+            return post_launch(ctx);
+        }
+        Geom gw;
+        GFB_CHECK(build_wide(g, uin, &gw));
+        for (size_t i = 0; i < ctx->slabs.size(); i++) {
+            Slab& s = ctx->slabs[i];
+            GFB_CUDA(ctx, cudaSetDevice(s.device));
+            launch_force_general(s.stream, gw, 2, g->tloc, 2, g->wide[i], uout ? (*uout)[i] : nullptr, zin ? (*zin)[i] : nullptr, zout ? (*zout)[i] : nullptr, fa);
+            GFB_CHECK(post_launch(ctx));
+        }
+        return GFB_OK;
     }
     fa.a *= fa.c_plaq;  // plaquette-only actions: the coefficient folds into the force scale and the Wilson kernels run
     fa.c_plaq = 1.0;
@@ -1282,7 +1348,7 @@ static int md_trajectory_impl(gfb_gauge* g, gfb_mom* p, double c_plaq, double c_
                 fa.c = (k == steps - 1) ? eps / 2 : eps;
                 GFB_CHECK(fused_pass(g, g->d, &ws->alt, &p->d, &p->d, fa));
                 std::swap(g->d, ws->alt);
-                g->halo_valid = true;  // exchanged inside the pass, overlapped with the interior slices
+                g->halo_valid = (c_rect == 0.0);  // exchanged inside the pass (the rectangle path works on wide copies instead)
             }
         } else {
             for (int k = 0; k < steps; k++) {
@@ -1291,7 +1357,7 @@ static int md_trajectory_impl(gfb_gauge* g, gfb_mom* p, double c_plaq, double c_
                 fa.c = eps;
                 GFB_CHECK(fused_pass(g, g->d, &ws->alt, &p->d, &p->d, fa));
                 std::swap(g->d, ws->alt);
-                g->halo_valid = true;  // exchanged inside the pass, overlapped with the interior slices
+                g->halo_valid = (c_rect == 0.0);  // exchanged inside the pass (the rectangle path works on wide copies instead)
             }
             GFB_CHECK(update_momenta_general(p, g, eps / 2, c_plaq, c_rect));
         }
@@ -1346,15 +1412,15 @@ static int flow_impl(gfb_gauge* g, double eps, int nsteps, double c_plaq, double
         GFB_CHECK(ensure_halo(g));
         fa.a = -eps; fa.b = 0.0; fa.c = 0.25; fa.read_z = false;
         GFB_CHECK(fused_pass(g, g->d, &ws->alt, nullptr, &ws->z, fa));
-        std::swap(g->d, ws->alt); g->halo_valid = true;
+        std::swap(g->d, ws->alt); g->halo_valid = (c_rect == 0.0);
         GFB_CHECK(ensure_halo(g));
         fa.a = -(8.0 / 9.0) * eps; fa.b = -17.0 / 36.0; fa.c = 1.0; fa.read_z = true;
         GFB_CHECK(fused_pass(g, g->d, &ws->alt, &ws->z, &ws->z, fa));
-        std::swap(g->d, ws->alt); g->halo_valid = true;
+        std::swap(g->d, ws->alt); g->halo_valid = (c_rect == 0.0);
         GFB_CHECK(ensure_halo(g));
         fa.a = -(3.0 / 4.0) * eps; fa.b = -1.0; fa.c = 1.0; fa.read_z = true;
         GFB_CHECK(fused_pass(g, g->d, &ws->alt, &ws->z, &ws->z, fa));
-        std::swap(g->d, ws->alt); g->halo_valid = true;
+        std::swap(g->d, ws->alt); g->halo_valid = (c_rect == 0.0);
     }
     return GFB_OK;
 }

@@ -12,7 +12,8 @@
 // force -> (momentum / flow field) -> exp kernel, like the Wilson path (kernels.cu): one launch per kick or RK3 stage instead of
 // ~40 whole-field kernels per rectangle staple.  Links are read with plain coalesced 128-bit loads (the t-marching tile kernel
 // covers the plaquette stencil only); all products are full 3x3 (no unitarity assumption).  Rectangles reach two sites away, so
-// these kernels run on single-slab contexts (one GPU); on a t-slab decomposition the API returns GFB_ERR_ARG.
+// on a t-slab decomposition the API first assembles a "wide" copy of the slab with two halo slices on either side in natural
+// t order (api.cu, build_wide): the kernels then read links at wide slice t and write their results at slab slice t - t_shift.
 #include "gfb_internal.h"
 #include "stencil.cuh"
 #include "su3.cuh"
@@ -100,19 +101,21 @@ __device__ __forceinline__ void m3_axpy(M3& acc, double a, const M3& m) {
 // Z' = a * TAcoeffs(U_mu (c_plaq V_plaq + c_rect V_rect)^dag) + b * Z ;  Uout_mu = exp(c Z') Uin_mu
 template <bool READ_Z, bool WRITE_Z, bool DO_EXP>
 __global__ void __launch_bounds__(128, 3)
-k_force_general(Geom g, const double2* __restrict__ uin, double2* __restrict__ uout, const double* __restrict__ zin, double* __restrict__ zout,
-                double a, double b, double c, double c_plaq, double c_rect) {
+k_force_general(Geom g, int t_begin, int t_count, int t_shift, const double2* __restrict__ uin, double2* __restrict__ uout, const double* __restrict__ zin,
+                double* __restrict__ zout, double a, double b, double c, double c_plaq, double c_rect) {
     const int mu = threadIdx.y;
     const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= (long)g.v3 * g.tloc) return;
-    const Coord x = decode_site(g, n, 0, g.tloc);
+    if (n >= (long)g.v3 * t_count) return;
+    const Coord x = decode_site(g, n, t_begin, t_count);
+    Coord xo = x;  // where the results go: the slab's own slice numbering
+    xo.t -= t_shift;
     M3 v = m3_zero();
     if (c_plaq != 0.0) m3_axpy(v, c_plaq, staple_sum<true>(uin, g, x, mu));
     if (c_rect != 0.0) m3_axpy(v, c_rect, rect_staple_sum(uin, g, x, mu));
     const M3 umu = load_link(uin, g, x, mu);
     double z[8];
     ta_coeffs_nd(umu, v, z);
-    const unsigned zo = mom_offset(g, x, mu);
+    const unsigned zo = mom_offset(g, xo, mu);
     const unsigned zs = (unsigned)g.v3;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -121,15 +124,15 @@ k_force_general(Geom g, const double2* __restrict__ uin, double2* __restrict__ u
         z[k] = w;
         if (WRITE_Z) zout[zo + k * zs] = w;
     }
-    if (DO_EXP) store_link(uout, g, x, mu, mul_nn(exp_ta(z, c), umu));
+    if (DO_EXP) store_link(uout, g, xo, mu, mul_nn(exp_ta(z, c), umu));
 }
 
 // per site: sum_{mu<nu} Re tr P_munu  and  sum over the 12 rectangle loops of Re tr  (evaluate_GaugeAction's two building blocks)
-__global__ void __launch_bounds__(128) k_loop_sums(Geom g, const double2* __restrict__ u, double* __restrict__ partial, int nblocks) {
+__global__ void __launch_bounds__(128) k_loop_sums(Geom g, int t_begin, int t_count, const double2* __restrict__ u, double* __restrict__ partial, int nblocks) {
     const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
     double plaq = 0.0, rect = 0.0;
-    if (n < (long)g.v3 * g.tloc) {
-        const Coord x = decode_site(g, n, 0, g.tloc);
+    if (n < (long)g.v3 * t_count) {
+        const Coord x = decode_site(g, n, t_begin, t_count);
 #pragma unroll 1
         for (int mu = 0; mu < 3; mu++) {
 #pragma unroll 1
@@ -216,10 +219,11 @@ __device__ __forceinline__ void field_strength(const double2* __restrict__ u, co
 // q(x) = -Re sum_{mu nu rho sigma} eps tr(F_munu F_rhosigma) / (32 pi^2 n^2), n = loops per field strength.  With
 // F = sum_a c_a i lambda_a / 2:  tr(F F') = -(1/2) sum_a c_a c'_a, and the 24 permutations are 8 x (01|23) - (02|13) + (03|12).
 // density[site] (host order x fastest, then y, z, local t) gets `weight` times the kind's density added (improved = 5/3 clover - 1/12 rectangle)
-__global__ void __launch_bounds__(128) k_topological_density(Geom g, const double2* __restrict__ u, double* __restrict__ density, int kind, double weight, int accumulate) {
+__global__ void __launch_bounds__(128) k_topological_density(Geom g, int t_begin, int t_count, int t_shift, const double2* __restrict__ u, double* __restrict__ density, int kind,
+                                                             double weight, int accumulate) {
     const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= (long)g.v3 * g.tloc) return;
-    const Coord x = decode_site(g, n, 0, g.tloc);
+    if (n >= (long)g.v3 * t_count) return;
+    const Coord x = decode_site(g, n, t_begin, t_count);
     const int pairs[3][4] = {{0, 1, 2, 3}, {0, 2, 1, 3}, {0, 3, 1, 2}};
     double q = 0.0;
 #pragma unroll 1
@@ -236,7 +240,7 @@ __global__ void __launch_bounds__(128) k_topological_density(Geom g, const doubl
     const double rect_factor = kind == 2 ? 2.0 : 1.0;
     // -Re(8 * (-1/2) * q) / (32 pi^2 n^2)
     const double val = weight * rect_factor * 4.0 * q / (32.0 * 9.869604401089358 * nl * nl);
-    const size_t idx = (size_t)s3_of(g, x) + (size_t)g.v3 * x.t;
+    const size_t idx = (size_t)s3_of(g, x) + (size_t)g.v3 * (x.t - t_shift);
     density[idx] = accumulate ? density[idx] + val : val;
 }
 
@@ -249,11 +253,12 @@ __global__ void __launch_bounds__(256) k_sum_plain(const double* __restrict__ v,
 
 }  // namespace
 
-void launch_force_general(cudaStream_t st, const Geom& g, const double2* uin, double2* uout, const double* zin, double* zout, const FusedArgs& fa) {
-    const long nsites = (long)g.v3 * g.tloc;
+void launch_force_general(cudaStream_t st, const Geom& g, int t_begin, int t_count, int t_shift, const double2* uin, double2* uout, const double* zin, double* zout,
+                          const FusedArgs& fa) {
+    const long nsites = (long)g.v3 * t_count;
     if (nsites <= 0) return;
     dim3 block(32, 4), grid((unsigned)((nsites + 31) / 32));
-#define GFB_LAUNCH_FG(R, W, E) k_force_general<R, W, E><<<grid, block, 0, st>>>(g, uin, uout, zin, zout, fa.a, fa.b, fa.c, fa.c_plaq, fa.c_rect)
+#define GFB_LAUNCH_FG(R, W, E) k_force_general<R, W, E><<<grid, block, 0, st>>>(g, t_begin, t_count, t_shift, uin, uout, zin, zout, fa.a, fa.b, fa.c, fa.c_plaq, fa.c_rect)
     if (fa.read_z) {
         if (fa.do_exp) GFB_LAUNCH_FG(true, true, true);
         else GFB_LAUNCH_FG(true, true, false);
@@ -266,15 +271,16 @@ void launch_force_general(cudaStream_t st, const Geom& g, const double2* uin, do
 #undef GFB_LAUNCH_FG
 }
 
-void launch_loop_sums(cudaStream_t st, const Geom& g, const double2* u, double* partial, int* nblocks) {
-    const int nb = plaquette_blocks(g);
-    k_loop_sums<<<nb, 128, 0, st>>>(g, u, partial, nb);
+void launch_loop_sums(cudaStream_t st, const Geom& g, int t_begin, int t_count, const double2* u, double* partial, int* nblocks) {
+    const int nb = (int)(((long)g.v3 * t_count + 127) / 128);
+    k_loop_sums<<<nb, 128, 0, st>>>(g, t_begin, t_count, u, partial, nb);
     *nblocks = nb;
 }
 
-void launch_topological_density(cudaStream_t st, const Geom& g, const double2* u, double* density, int kind, double weight, bool accumulate) {
-    const int nb = plaquette_blocks(g);
-    k_topological_density<<<nb, 128, 0, st>>>(g, u, density, kind, weight, accumulate ? 1 : 0);
+void launch_topological_density(cudaStream_t st, const Geom& g, int t_begin, int t_count, int t_shift, const double2* u, double* density, int kind, double weight,
+                                bool accumulate) {
+    const int nb = (int)(((long)g.v3 * t_count + 127) / 128);
+    k_topological_density<<<nb, 128, 0, st>>>(g, t_begin, t_count, t_shift, u, density, kind, weight, accumulate ? 1 : 0);
 }
 
 void launch_sum_plain(cudaStream_t st, const double* v, size_t n, double* partial, int* nblocks) {

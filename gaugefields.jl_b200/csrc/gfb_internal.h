@@ -79,6 +79,7 @@ struct gfb_gauge {
     // workspaces owned by the handle: double buffer of the fused updates, flow field Z
     std::vector<double2*> alt;
     std::vector<double*> z;
+    std::vector<double2*> wide;  // t-slab decompositions, general-action path: tloc + 4 slices (two halo slices either side, natural order)
     size_t elems_per_slab() const { return (size_t)(tloc + (has_halo ? 2 : 0)) * 36 * (size_t)nx * ny * nz; }
     size_t slice_elems() const { return (size_t)36 * nx * ny * nz; }
 };
@@ -158,12 +159,15 @@ void launch_force_fused(cudaStream_t st, const Geom& g, int t_begin, int t_count
 // persistent t-marching shared-memory variant of launch_force_fused (tmarch.cu); false = launch not covered, nothing launched
 bool launch_tmarch_fused(cudaStream_t st, const Geom& g, int t_begin, int t_count, const double2* uin, double2* uout, const double* zin, double* zout,
                          const FusedArgs& fa);
-// general-action path (general.cu): single-slab geometries only
-void launch_force_general(cudaStream_t st, const Geom& g, const double2* uin, double2* uout, const double* zin, double* zout, const FusedArgs& fa);
+// general-action path (general.cu).  Links are read at slices [t_begin, t_begin + t_count) of `u` (whose neighbours two slices away
+// must be addressable: a single-slab field, or the wide copy of a slab) and results are written at slice t - t_shift.
+void launch_force_general(cudaStream_t st, const Geom& g, int t_begin, int t_count, int t_shift, const double2* uin, double2* uout, const double* zin, double* zout,
+                          const FusedArgs& fa);
 // partial[0..nb) = block sums of sum_{mu<nu} Re tr P, partial[nb..2nb) = block sums of Re tr over the 12 rectangle loops
-void launch_loop_sums(cudaStream_t st, const Geom& g, const double2* u, double* partial, int* nblocks);
-// kind 0 plaquette, 1 clover, 2 rectangle field strengths; density[x + nx*(y + ny*(z + nz*t))] (+)= weight * q(x)
-void launch_topological_density(cudaStream_t st, const Geom& g, const double2* u, double* density, int kind, double weight, bool accumulate);
+void launch_loop_sums(cudaStream_t st, const Geom& g, int t_begin, int t_count, const double2* u, double* partial, int* nblocks);
+// kind 0 plaquette, 1 clover, 2 rectangle field strengths; density[x + nx*(y + ny*(z + nz*(t - t_shift)))] (+)= weight * q(x)
+void launch_topological_density(cudaStream_t st, const Geom& g, int t_begin, int t_count, int t_shift, const double2* u, double* density, int kind, double weight,
+                                bool accumulate);
 void launch_sum_plain(cudaStream_t st, const double* v, size_t n, double* partial, int* nblocks);
 // peer-store halo exchange: tell both ring neighbours that pass `serial` is complete here, then wait for theirs
 void launch_halo_signal_wait(cudaStream_t st, unsigned* peer_flag_prev, unsigned* peer_flag_next, unsigned* my_flags, unsigned serial);

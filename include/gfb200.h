@@ -153,8 +153,8 @@ int gfb_wilson_dSdU(gfb_gauge* d, gfb_gauge* g, double beta);
  * A GaugeAction with the terms (c_plaq, plaquette + plaquette') and (c_rect, rectangular + rectangular')
  * (GaugeAction/push!, src/action/GaugeActions.jl:23-62; "rectangular" = the 1x2 and 2x1 loops of every plane,
  * src/autostaples/wilsonloops.jl:233-245).  dSdU_mu = c_plaq * (6 plaquette staples) + c_rect * (18 rectangle staples)
- * (calc_dSdUmu!, GaugeActions.jl:95-123).  c_rect = 0 runs the Wilson kernels; c_rect != 0 needs a single-GPU context
- * (GFB_ERR_ARG otherwise: the t-slab halo is one slice wide). */
+ * (calc_dSdUmu!, GaugeActions.jl:95-123).  c_rect = 0 runs the Wilson kernels.  On a t-slab decomposition the rectangle kernels
+ * work on a copy of each slab with two halo slices either side (the reference's NDW = 2 wing), so a slab needs >= 2 slices. */
 /* out2 = { sum_{x, mu<nu} Re tr P_munu, sum_x Re tr of the 12 rectangle loops }: evaluate_GaugeAction's building blocks
  * (GaugeActions.jl:132-142); Re evaluate_GaugeAction = 2 * (c_plaq * out2[0] + c_rect * out2[1]) */
 int gfb_loop_sums(gfb_gauge* g, double* out2);
@@ -170,7 +170,8 @@ int gfb_md_trajectory_general(gfb_gauge* g, gfb_mom* p, double c_plaq, double c_
  * ("plaquette", "rectangular"); (1, 0) is gfb_flow */
 int gfb_flow_general(gfb_gauge* g, double eps, int nsteps, double c_plaq, double c_rect);
 /* topological_charge(U; method) / topological_charge_density(U; method) (src/AbstractGaugefields.jl:1447-1490):
- * method 0 :plaquette, 1 :clover, 2 :improved (needs a single-GPU context).  host_density = Float64[NX,NY,NZ,NT]. */
+ * method 0 :plaquette, 1 :clover, 2 :improved.  host_density = Float64[NX,NY,NZ,NT]; the reference supports serial fields only
+ * (AbstractGaugefields.jl:1403-1434), this backend also t-slab decompositions. */
 enum gfb_topo_method { GFB_Q_PLAQUETTE = 0, GFB_Q_CLOVER = 1, GFB_Q_IMPROVED = 2 };
 int gfb_topological_charge(gfb_gauge* g, int method, double* out);
 int gfb_topological_charge_density(gfb_gauge* g, int method, double* host_density);

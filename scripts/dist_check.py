@@ -57,6 +57,24 @@ def main():
     assert np.abs(U.to_host(local=True) - Uo[:, t0:t1]).max() < 1e-12
     e = gfb200.energy_density(U)
     assert abs(e - oracle.energy_density_clover(Uo, dims)) < 1e-11 * max(1.0, abs(e))
+    # general-action path on one process per GPU: rectangle force, trajectory and improved topological charge across slab faces
+    cp, cr = 4.5 / 2 * (1 + 8 / 12), 4.5 / 2 * (-1 / 12)
+    pl, rl = gfb200.make_loops_fromname("plaquette"), gfb200.make_loops_fromname("rectangular")
+    sym = gfb200.GaugeAction(U).push(cp, pl + pl.adjoint()).push(cr, rl + rl.adjoint())
+    U.upload(Uh)
+    F = gfb200.gauge_momenta(U)
+    gfb200.md_force_(F, sym, U)
+    Fg = oracle.force_general(Uh, dims, cp, cr)
+    assert np.abs(F.to_host(local=True) - Fg[:, t0:t1]).max() < 1e-12 * np.abs(Fg).max()
+    P.upload(Ph)
+    md = gfb200.md_driver(U, sym, steps=4, trajectory_length=0.2, integrator=gfb200.QPQ, fused=True)
+    res = gfb200.md_trajectory_(U, P, md)
+    Uo, Po = Uh.copy(), Ph.copy()
+    H0, H1 = oracle.md_trajectory_general(Uo, Po, dims, cp, cr, 4, 0.2, 0)
+    assert abs(res.delta_hamiltonian - (H1 - H0)) < max(1e-9, 4e-14 * abs(H0)), (res.delta_hamiltonian, H1 - H0)
+    assert np.abs(U.to_host(local=True) - Uo[:, t0:t1]).max() < 1e-11
+    q = gfb200.topological_charge(U, method="improved")
+    assert abs(q - oracle.topological_charge_density(Uo, dims, 2).sum()) < 1e-12 * max(1.0, abs(q))
     dist.barrier()
     if rank == 0:
         print("dist_check ok: %d ranks" % world)

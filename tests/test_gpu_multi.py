@@ -96,6 +96,56 @@ def test_two_slabs_match_oracle(backend2, oracle, dims, monkeypatch):
     assert np.abs(F.to_host() - Fw).max() / np.abs(Fw).max() < 1e-12
 
 
+@pytest.mark.parametrize("dims", [(4, 6, 4, 8), (8, 4, 2, 4)])
+def test_general_action_across_slabs(backend2, oracle, dims):
+    """Rectangle terms reach two slices across a slab face: the general-action kernels run on a wide copy of each slab
+    (two halo slices either side, csrc/api.cu build_wide).  (8, 4, 2, 4) has two slices per slab: both halos are the whole
+    neighbour."""
+    import gfb200
+
+    cp, cr = 4.5 / 2 * (1 + 8 / 12), 4.5 / 2 * (-1 / 12)
+    Uh = oracle.hot_start_philox(dims, 77)
+    for _ in range(3):
+        oracle.flow_step(Uh, dims, 0.02)
+    U = gfb200.gauge_configuration(dims, backend=backend2).upload(Uh)
+    p, r = gfb200.make_loops_fromname("plaquette"), gfb200.make_loops_fromname("rectangular")
+    action = gfb200.GaugeAction(U).push(cp, p + p.adjoint()).push(cr, r + r.adjoint())
+    F = gfb200.gauge_momenta(U)
+    gfb200.md_force_(F, action, U)
+    want = oracle.force_general(Uh, dims, cp, cr)
+    assert np.abs(F.to_host() - want).max() < 1e-12 * np.abs(want).max()
+    sp, sr = oracle.loop_sums(Uh, dims)
+    assert abs(gfb200.evaluate_GaugeAction(action, U).real - 2 * (cp * sp + cr * sr)) < 1e-12 * (abs(cp * sp) + abs(cr * sr))
+    Ph = oracle.gaussian_momenta(dims, 0x5678, 5)
+    for integ in (gfb200.QPQ, gfb200.PQP):
+        for fused in (True, False):
+            U.upload(Uh)
+            P = gfb200.gauge_momenta(U).upload(Ph)
+            md = gfb200.md_driver(U, action, steps=4, trajectory_length=0.2, integrator=integ, fused=fused)
+            res = gfb200.md_trajectory_(U, P, md)
+            Uo, Po = Uh.copy(), Ph.copy()
+            H0, H1 = oracle.md_trajectory_general(Uo, Po, dims, cp, cr, 4, 0.2, integ.code)
+            assert abs(res.delta_hamiltonian - (H1 - H0)) < 1e-9
+            assert np.abs(U.to_host() - Uo).max() < 1e-11
+            assert np.abs(P.to_host() - Po).max() < 1e-10
+    # a Wilson pass right after a rectangle pass must see a fresh one-slice halo (the wide path does not fill it)
+    wil = gfb200.GaugeAction(U).push(2.9, p + p.adjoint())
+    gfb200.md_force_(F, wil, U)
+    Fw = oracle.force(Uo, dims, 5.8)
+    assert np.abs(F.to_host() - Fw).max() < 1e-12 * np.abs(Fw).max()
+    U.upload(Uh)
+    gfb200.flow_(U, gfb200.Gradientflow_general(U, ["plaquette", "rectangular"], [5 / 3, -1 / 12], Nflow=2, eps=0.01))
+    Uf = Uh.copy()
+    for _ in range(2):
+        oracle.flow_step_general(Uf, dims, 0.01, 5 / 3, -1 / 12)
+    assert np.abs(U.to_host() - Uf).max() < 1e-12
+    for code, method in enumerate(("plaquette", "clover", "improved")):
+        wq = oracle.topological_charge_density(Uf, dims, code)
+        got = gfb200.topological_charge_density(U, method=method)
+        assert np.abs(got - wq).max() < 1e-13 * max(1.0, np.abs(wq).max())
+        assert abs(gfb200.topological_charge(U, method=method) - wq.sum()) < 1e-12 * max(1.0, np.abs(wq).sum())
+
+
 def test_primitive_table_across_slabs(backend2, oracle):
     """shifted / adjoint mul! and tr with t-shifts that cross the slab faces (field-level halo exchange)."""
     import gfb200 as g
