@@ -397,6 +397,7 @@ static int post_launch(gfb_ctx* ctx, int nlaunch = 1) {
 extern "C" {
 
 static int build_wide(gfb_gauge* g, const std::vector<double2*>& src, Geom* wide_geom);
+static int links_are_unitary(gfb_gauge* g, bool* yes);
 
 int gfb_version(void) { return 100; }
 
@@ -1020,13 +1021,15 @@ int gfb_energy_density(gfb_gauge* g, int kind, double* out) {
     }
     if (kind != GFB_E_CLOVER) return fail(ctx, GFB_ERR_ARG, "unknown energy-density kind");
     GFB_CHECK(ensure_halo(g));
+    bool unitary = true;
+    GFB_CHECK(links_are_unitary(g, &unitary));
     for (size_t i = 0; i < ctx->slabs.size(); i++) {
         Slab& s = ctx->slabs[i];
         Geom geo = geom_of(g, i);
         GFB_CHECK(ensure_partial(ctx, s, (size_t)plaquette_blocks(geo) * 2 + 16));
         GFB_CUDA(ctx, cudaSetDevice(s.device));
         int nb = 0;
-        launch_clover_energy(s.stream, geo, g->d[i], s.d_partial, &nb);
+        launch_clover_energy(s.stream, geo, g->d[i], s.d_partial, &nb, !unitary);
         launch_final_reduce(s.stream, s.d_partial, nb, s.d_result);
         GFB_CHECK(post_launch(ctx, 2));
     }

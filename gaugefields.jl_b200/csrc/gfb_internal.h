@@ -177,7 +177,7 @@ void launch_final_max(cudaStream_t st, const double* partial, int n, double* out
 void launch_update_links(cudaStream_t st, const Geom& g, int t_begin, int t_count, const double2* uin, double2* uout, const double* z, double c);
 void launch_plaquette(cudaStream_t st, const Geom& g, const double2* u, double* partial, int* nblocks);
 void launch_sumsq(cudaStream_t st, const double* p, size_t n, double* partial, int* nblocks);
-void launch_clover_energy(cudaStream_t st, const Geom& g, const double2* u, double* partial, int* nblocks);
+void launch_clover_energy(cudaStream_t st, const Geom& g, const double2* u, double* partial, int* nblocks, bool full3);
 void launch_polyakov(cudaStream_t st, const Geom& g, const double2* u, const double2* pin, double2* pout, double* partial, int* nblocks);  // two interleaved partial arrays
 void launch_final_reduce(cudaStream_t st, const double* partial, int n, double* out);
 int plaquette_blocks(const Geom& g);
