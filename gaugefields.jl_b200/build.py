@@ -10,7 +10,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["kernels.cu", "tmarch.cu", "stout.cu", "primitives.cu", "general.cu", "api.cu"]
+SOURCES = ["kernels.cu", "tmarch.cu", "stout.cu", "primitives.cu", "general.cu", "heatbath.cu", "api.cu"]
 HEADERS = ["su3.cuh", "lattice.cuh", "stencil.cuh", "tmarch_geom.h", "gfb_internal.h", os.path.join("..", "..", "include", "gfb200.h")]
 # GFB200_VARIANT=<name> + GFB200_NVCC_EXTRA="-D..." build a tuning variant next to the default library
 VARIANT = os.environ.get("GFB200_VARIANT", "")

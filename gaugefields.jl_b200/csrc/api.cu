@@ -1432,6 +1432,45 @@ int gfb_flow(gfb_gauge* g, double eps, int nsteps) { return flow_impl(g, eps, ns
 // ("plaquette", "rectangular"): F = TAcoeffs(U dSdU), the same RK3 scheme; (1, 0) is the Wilson flow
 int gfb_flow_general(gfb_gauge* g, double eps, int nsteps, double c_plaq, double c_rect) { return flow_impl(g, eps, nsteps, c_plaq, c_rect); }
 
+// heatbath!(U, ::Heatbath) / overrelaxation!(U, ...) for the Wilson action (src/heatbath/heatbathmodule.jl:481-650, 1799-1860):
+// for every direction and both checkerboard colours, refresh the halo, then update every link of that colour in place
+static int heatbath_sweep(gfb_gauge* g, double beta, uint64_t seed, uint64_t sweep, int rng_alg, bool overrelax) {
+    if (!g) return fail(nullptr, GFB_ERR_ARG, "null argument");
+    gfb_ctx* ctx = g->ctx;
+    if (rng_alg != GFB_PHILOX4X32) return fail(ctx, GFB_ERR_ARG, "the B200 backend implements the Philox4x32 site RNG");
+    if ((g->nx | g->ny | g->nz | g->nt) & 1) return fail(ctx, GFB_ERR_ARG, "the checkerboard update needs even lattice extents");
+    if (!overrelax && !(beta > 0.0 && std::isfinite(beta))) return fail(ctx, GFB_ERR_ARG, "beta must be positive and finite");
+    for (auto& s : ctx->slabs) {
+        GFB_CUDA(ctx, cudaSetDevice(s.device));
+        GFB_CUDA(ctx, cudaMemsetAsync(s.d_flags + 8, 0, sizeof(int), s.stream));
+    }
+    for (int mu = 0; mu < 4; mu++)
+        for (int colour = 0; colour < 2; colour++) {
+            GFB_CHECK(ensure_halo(g));
+            for (size_t i = 0; i < ctx->slabs.size(); i++) {
+                Slab& s = ctx->slabs[i];
+                GFB_CUDA(ctx, cudaSetDevice(s.device));
+                launch_heatbath(s.stream, geom_of(g, i), g->d[i], mu, colour, beta, seed, sweep, overrelax, reinterpret_cast<int*>(s.d_flags + 8));
+                GFB_CHECK(post_launch(ctx));
+            }
+            g->halo_valid = false;
+        }
+    g->unitary = 1;  // every updated link was reunitarised; the update preserves the group manifold
+    int total = 0;
+    for (auto& s : ctx->slabs) {
+        int f = 0;
+        GFB_CUDA(ctx, cudaSetDevice(s.device));
+        GFB_CUDA(ctx, cudaMemcpyAsync(&f, s.d_flags + 8, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+        GFB_CUDA(ctx, cudaStreamSynchronize(s.stream));
+        total += f;
+    }
+    if (total) return fail(ctx, GFB_ERR_NUMERIC, overrelax ? "overrelaxation normalization failed at " + std::to_string(total) + " site(s)"
+                                                           : "SU(3) heatbath failed at " + std::to_string(total) + " site(s) after 100000 tries");
+    return GFB_OK;
+}
+int gfb_heatbath(gfb_gauge* g, double beta, uint64_t seed, uint64_t sweep, int rng_alg) { return heatbath_sweep(g, beta, seed, sweep, rng_alg, false); }
+int gfb_overrelaxation(gfb_gauge* g, double beta, uint64_t seed, uint64_t sweep, int rng_alg) { return heatbath_sweep(g, beta, seed, sweep, rng_alg, true); }
+
 int gfb_stout_forward(gfb_gauge* out, gfb_gauge* in, double rho, gfb_mom* q) {
     if (!out || !in) return fail(in ? in->ctx : nullptr, GFB_ERR_ARG, "null argument");
     gfb_ctx* ctx = in->ctx;

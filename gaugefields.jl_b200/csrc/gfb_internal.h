@@ -169,6 +169,9 @@ void launch_loop_sums(cudaStream_t st, const Geom& g, int t_begin, int t_count, 
 void launch_topological_density(cudaStream_t st, const Geom& g, int t_begin, int t_count, int t_shift, const double2* u, double* density, int kind, double weight,
                                 bool accumulate);
 void launch_sum_plain(cudaStream_t st, const double* v, size_t n, double* partial, int* nblocks);
+// one checkerboard colour of direction mu: Cabibbo-Marinari heatbath (Kennedy-Pendleton) or overrelaxation, in place (heatbath.cu)
+void launch_heatbath(cudaStream_t st, const Geom& g, double2* u, int mu, int colour, double beta, unsigned long long seed, unsigned long long sweep, bool overrelax,
+                     int* failures);
 // peer-store halo exchange: tell both ring neighbours that pass `serial` is complete here, then wait for theirs
 void launch_halo_signal_wait(cudaStream_t st, unsigned* peer_flag_prev, unsigned* peer_flag_next, unsigned* my_flags, unsigned serial);
 // max over the local links of |U U^dag - 1|_max and |det U - 1| -> partial[0..nblocks) (block maxima)

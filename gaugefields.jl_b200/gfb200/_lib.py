@@ -74,6 +74,8 @@ SIGNATURES = {
     "gfb_flow_general": (c_int, [c_void_p, c_double, c_int, c_double, c_double]),
     "gfb_topological_charge": (c_int, [c_void_p, c_int, P(c_double)]),
     "gfb_topological_charge_density": (c_int, [c_void_p, c_int, c_void_p]),
+    "gfb_heatbath": (c_int, [c_void_p, c_double, c_u64, c_u64, c_int]),
+    "gfb_overrelaxation": (c_int, [c_void_p, c_double, c_u64, c_u64, c_int]),
     # primitive table
     "gfb_field_alloc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, P(c_void_p)]),
     "gfb_field_view": (c_int, [c_void_p, c_int, P(c_void_p)]),

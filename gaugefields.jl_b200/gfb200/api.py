@@ -29,7 +29,7 @@ __all__ = [
     "energy_density", "stout_smearing", "smear", "Philox4x32", "GfbError", "gauge_lattice_size",
     "gauge_num_colors", "gauge_process_grid", "download_configuration", "upload_configuration_",
     "calc_smearedU", "back_prop", "calc_dSdU", "stout_force_", "evaluate_GaugeAction", "StoutWorkspace", "stout_hamiltonian", "reunitarize_", "normalize_U_", "MDActionSet", "MDForceGroup", "SextonWeingarten",
-    "Gradientflow_general", "topological_charge", "topological_charge_density",
+    "Gradientflow_general", "topological_charge", "topological_charge_density", "Heatbath", "heatbath_", "overrelaxation_",
     "MatrixField", "link_field", "shift_U", "clear_U_", "unit_U_", "substitute_U_", "mul_", "add_U_", "tr",
     "Traceless_antihermitian_", "Traceless_antihermitian_add_", "exptU_",
 ]
@@ -795,6 +795,32 @@ def flow_(U, g):
         U.backend.call("gfb_flow_general", U._h, g.eps, g.Nflow, g.c_plaq, g.c_rect)
     else:
         U.backend.call("gfb_flow", U._h, g.eps, g.Nflow)
+    return U
+
+
+class Heatbath:
+    """Heatbath(U, beta; seed, sweep=0, rng_algorithm=Philox4x32()) (src/heatbath/heatbathmodule.jl:55-99): the Wilson-action
+    heatbath / overrelaxation updater.  `sweep` counts the sweeps done and keys their random streams."""
+
+    def __init__(self, U, beta, seed=0, sweep=0, rng_algorithm=Philox4x32):
+        if rng_algorithm not in (Philox4x32,) and not isinstance(rng_algorithm, Philox4x32):
+            raise ValueError("the B200 backend implements the Philox4x32 site RNG")
+        if not (beta > 0 and math.isfinite(beta)):
+            raise ValueError("beta must be positive and finite; got %s" % (beta,))
+        self.beta, self.seed, self.sweep, self.overrelaxation_sweep = float(beta), int(seed), int(sweep), int(sweep)
+
+
+def heatbath_(U, h):
+    """heatbath!(U, h::Heatbath) (src/heatbath/heatbathmodule.jl:843-845): one sweep over 4 directions x 2 colours."""
+    U.backend.call("gfb_heatbath", U._h, h.beta, h.seed, h.sweep, 0)
+    h.sweep += 1
+    return U
+
+
+def overrelaxation_(U, h):
+    """overrelaxation!(U, h::Heatbath) (src/heatbath/heatbathmodule.jl:847-852): one microcanonical sweep."""
+    U.backend.call("gfb_overrelaxation", U._h, h.beta, h.seed, h.overrelaxation_sweep, 0)
+    h.overrelaxation_sweep += 1
     return U
 
 

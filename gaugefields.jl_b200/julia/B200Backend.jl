@@ -526,6 +526,22 @@ function b200_kick_from_dSdU!(P::B200Momenta, U::B200Links, dSdU::B200Links, fac
     return P
 end
 
+# ---- heatbath / overrelaxation: heatbath!(U, h::Heatbath), overrelaxation!(U, h) (src/heatbath/heatbathmodule.jl:843-852) --------
+# One sweep = 4 directions x 2 checkerboard colours in the library; `h.sweep` / `h.overrelaxation_sweep` key the streams and advance
+# as in the reference (Heatbath fields β, seed, sweep, overrelaxation_sweep: heatbathmodule.jl:55-99).
+function heatbath!(U::B200Links, h::Heatbath)
+    g = _b200_handle(U)
+    _gfb_check(ccall((:gfb_heatbath, LIBGFB200), Cint, (Ptr{Cvoid}, Cdouble, UInt64, UInt64, Cint), g.ptr, Float64(h.β), UInt64(h.seed), UInt64(h.sweep), 0), g.ctx.ptr)
+    h.sweep += 1
+    return U
+end
+function overrelaxation!(U::B200Links, h::Heatbath)
+    g = _b200_handle(U)
+    _gfb_check(ccall((:gfb_overrelaxation, LIBGFB200), Cint, (Ptr{Cvoid}, Cdouble, UInt64, UInt64, Cint), g.ptr, Float64(h.β), UInt64(h.seed), UInt64(h.overrelaxation_sweep), 0), g.ctx.ptr)
+    h.overrelaxation_sweep += 1
+    return U
+end
+
 # ---- primitive table on Gaugefields_4D_B200 ---------------------------------------------------------------------
 # Lazy shift / adjoint views mirror Shifted_/Adjoint_Gaugefields_4D_MPILattice (gaugefields_4D_MPILattice.jl:647-689): the
 # library's gfb_mul / gfb_field_copy take the shift and the dagger flag of each operand, so no shifted copy is ever made.

@@ -42,7 +42,8 @@ enum gfb_status {
     GFB_ERR_ARG = 1,     /* invalid argument (the Julia wrapper rethrows ArgumentError, molecular_dynamics.jl:447-465) */
     GFB_ERR_CUDA = 2,    /* CUDA runtime error */
     GFB_ERR_NCCL = 3,    /* NCCL error */
-    GFB_ERR_NODEVICE = 4 /* no usable GPU: there is no CPU fallback */
+    GFB_ERR_NODEVICE = 4, /* no usable GPU: there is no CPU fallback */
+    GFB_ERR_NUMERIC = 5   /* a site update failed (heatbath acceptance / normalisation), as the reference's error() at heatbathmodule.jl:1852-1857 */
 };
 
 enum gfb_integrator { GFB_QPQ = 0, GFB_PQP = 1 }; /* md_step! src/molecular_dynamics.jl:604-616 */
@@ -175,6 +176,15 @@ int gfb_flow_general(gfb_gauge* g, double eps, int nsteps, double c_plaq, double
 enum gfb_topo_method { GFB_Q_PLAQUETTE = 0, GFB_Q_CLOVER = 1, GFB_Q_IMPROVED = 2 };
 int gfb_topological_charge(gfb_gauge* g, int method, double* out);
 int gfb_topological_charge_density(gfb_gauge* g, int method, double* host_density);
+
+/* ---- heatbath and overrelaxation (the other quenched updater) ---------------------------------------------------------------
+ * heatbath!(U, h::Heatbath) / overrelaxation!(U, h) for the Wilson action (src/heatbath/heatbathmodule.jl:481-650): one sweep =
+ * 4 directions x 2 checkerboard colours; SU(3) by the subgroup sequence (1,2),(2,3),(1,3) with Kennedy-Pendleton sampling
+ * (src/heatbath/portable/kernels.jl:63-270); overrelaxation by three random-subgroup reflections (heatbathmodule.jl:1243-1322).
+ * Streams are keyed by (seed, sweep, direction, colour, subgroup) and the GLOBAL site, like the reference's
+ * (heatbathmodule.jl:1815-1818): a sweep does not depend on the t-slab decomposition.  Even extents required. */
+int gfb_heatbath(gfb_gauge* g, double beta, uint64_t seed, uint64_t sweep, int rng_alg);
+int gfb_overrelaxation(gfb_gauge* g, double beta, uint64_t seed, uint64_t sweep, int rng_alg);
 
 /* ---- primitive table ---------------------------------------------------------------------------
  * The element-wise operations that Gaugefields.jl's generic (un-fused) algorithms are written in; each forwards to one

@@ -972,3 +972,136 @@ void orc_topological_charge_density(const double* U, const int* dims, int method
 }
 
 }  // extern "C"
+
+// ================================================================================================
+// Heatbath and overrelaxation for the SU(3) Wilson action.  Restates the site algorithm of the reference
+// (src/heatbath/portable/kernels.jl:14-270: project_onto_SU2!, _su2_update_kp_core!, _su3_update_subgroup!, the fixed subgroup
+// sequence (1,2),(2,3),(1,3); overrelaxation: src/heatbath/heatbathmodule.jl:1243-1322) and the sweep order of
+// heatbath!(U, ::Heatbath) (direction, then even / odd sites, :481-650).  The random STREAMS are this repository's
+// (Philox keyed by seed, sweep, direction, colour, subgroup and global site; the reference's bits come from the un-vendored
+// LatticeMatrices.jl -- parity unpinned), drawn in the reference's order: (R, R'), (R'', R''') per try, then
+// (phi, cos theta).
+// ================================================================================================
+namespace {
+
+const uint32_t TAG_HEATBATH = 0x48424154u, TAG_OVERRELAX = 0x4f56524cu;
+
+inline void hb_stream_key(uint64_t seed, uint64_t sweep, uint32_t direction, uint32_t colour, uint32_t subgroup, uint32_t tag, uint32_t key[2]) {
+    uint32_t ctr[4] = {(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)sweep, (uint32_t)(sweep >> 32)};
+    uint32_t k[2] = {tag, direction | (colour << 8) | (subgroup << 16)};
+    uint32_t o[4];
+    philox4x32_10(ctr, k, o);
+    key[0] = o[0]; key[1] = o[1];
+}
+
+struct S2 { cd a[2][2]; };
+
+inline S2 sub_projected(const M3& uv, int n, int m) {
+    S2 s;
+    s.a[0][0] = uv.a[n][n]; s.a[0][1] = uv.a[n][m]; s.a[1][0] = uv.a[m][n]; s.a[1][1] = uv.a[m][m];
+    cd alpha = 0.5 * s.a[0][0] + 0.5 * std::conj(s.a[1][1]);
+    cd beta = 0.5 * s.a[1][0] - 0.5 * std::conj(s.a[0][1]);
+    s.a[0][0] = alpha; s.a[1][0] = beta; s.a[0][1] = -std::conj(beta); s.a[1][1] = std::conj(alpha);
+    return s;
+}
+inline M3 embed(const S2& k, int n, int m) {
+    M3 a = ident3();
+    a.a[n][n] = k.a[0][0]; a.a[n][m] = k.a[0][1]; a.a[m][n] = k.a[1][0]; a.a[m][m] = k.a[1][1];
+    return a;
+}
+inline S2 mul2(const S2& x, const S2& y) {
+    S2 r;
+    for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) r.a[i][j] = x.a[i][0] * y.a[0][j] + x.a[i][1] * y.a[1][j];
+    return r;
+}
+
+// _su2_update_kp_core! (portable/kernels.jl:63-150)
+inline bool su2_update_kp(const S2& V, double beta, const uint32_t key[2], uint64_t gsite, S2* out) {
+    const double rho0 = (V.a[0][0] + V.a[1][1]).real() / 2, rho1 = -(V.a[0][1] + V.a[1][0]).imag() / 2;
+    const double rho2 = (V.a[1][0] - V.a[0][1]).real() / 2, rho3 = (V.a[1][1] - V.a[0][0]).imag() / 2;
+    const double rho = std::sqrt(rho0 * rho0 + rho1 * rho1 + rho2 * rho2 + rho3 * rho3);
+    const cd det = V.a[0][0] * V.a[1][1] - V.a[0][1] * V.a[1][0];
+    S2 V0;
+    V0.a[0][0] = rho * V.a[1][1] / det; V0.a[0][1] = -rho * V.a[0][1] / det;
+    V0.a[1][0] = -rho * V.a[1][0] / det; V0.a[1][1] = rho * V.a[0][0] / det;
+    const double k = 2.0 * (beta / 3.0) * rho;
+    uint32_t draw = 0;
+    double delta = 0.0;
+    bool accepted = false;
+    for (int tries = 0; tries < 100000; tries++) {
+        double R, Rp, Rpp, Rppp;
+        site_uniform_pair(key, gsite, draw++, &R, &Rp);
+        site_uniform_pair(key, gsite, draw++, &Rpp, &Rppp);
+        const double X = -std::log(1.0 - R) / k, Xp = -std::log(1.0 - Rp) / k;
+        const double c = std::cos(2.0 * M_PI * Rpp);
+        delta = Xp + X * c * c;
+        if (Rppp * Rppp <= 1.0 - 0.5 * delta) { accepted = true; break; }
+    }
+    if (!accepted) return false;
+    const double a1 = 1.0 - delta, rr = std::sqrt(std::max(1.0 - a1 * a1, 0.0));
+    double uphi, ucos;
+    site_uniform_pair(key, gsite, draw++, &uphi, &ucos);
+    const double phi = 2.0 * M_PI * uphi, costheta = 2.0 * (ucos - 0.5), sintheta = std::sqrt(std::max(1.0 - costheta * costheta, 0.0));
+    const double a2 = rr * std::cos(phi) * sintheta, a3 = rr * std::sin(phi) * sintheta, a4 = rr * costheta;
+    S2 temp;
+    temp.a[0][0] = cd(a1, a4); temp.a[0][1] = cd(a3, a2); temp.a[1][0] = cd(-a3, a2); temp.a[1][1] = cd(a1, -a4);
+    S2 U = mul2(temp, V0);
+    const cd alpha = 0.5 * U.a[0][0] + 0.5 * std::conj(U.a[1][1]), b2 = 0.5 * U.a[1][0] - 0.5 * std::conj(U.a[0][1]);
+    const double detU = std::norm(alpha) + std::norm(b2);
+    out->a[0][0] = alpha / detU; out->a[1][0] = b2 / detU; out->a[0][1] = -std::conj(b2) / detU; out->a[1][1] = std::conj(alpha) / detU;
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+// one sweep; returns the number of failed sites (0 = ok).  overrelax = 0: heatbath, 1: overrelaxation
+int orc_heatbath_sweep(double* U, const int* dims, double beta, uint64_t seed, uint64_t sweep, int overrelax) {
+    Lat L(dims);
+    int failures = 0;
+    for (int mu = 0; mu < 4; mu++)
+        for (int colour = 0; colour < 2; colour++) {
+            uint32_t keys[3][2];
+            for (uint32_t s = 0; s < 3; s++) hb_stream_key(seed, sweep, (uint32_t)(mu + 1), (uint32_t)colour, s, overrelax ? TAG_OVERRELAX : TAG_HEATBATH, keys[s]);
+            // in place: the staples of a link of one colour hold no mu-link of that colour
+#pragma omp parallel for reduction(+ : failures)
+            for (long s = 0; s < L.V; s++) {
+                int x[4];
+                L.coord(s, x);
+                if (((x[0] + x[1] + x[2] + x[3]) & 1) != colour) continue;
+                const M3 V = dag(staple_sum(U, L, x, mu));  // tr(u V) = the six plaquettes through the link
+                M3 u = getU(U, L, mu, s);
+                bool ok = true;
+                if (!overrelax) {
+                    const int sub[3][2] = {{0, 1}, {1, 2}, {0, 2}};
+                    for (int k = 0; k < 3 && ok; k++) {
+                        const S2 w = sub_projected(mul(u, V), sub[k][0], sub[k][1]);
+                        S2 K;
+                        ok = su2_update_kp(w, beta, keys[k], (uint64_t)s, &K);
+                        if (ok) u = mul(embed(K, sub[k][0], sub[k][1]), u);
+                    }
+                } else {
+                    for (uint32_t k = 0; k < 3 && ok; k++) {
+                        double u0, u1;
+                        site_uniform_pair(keys[0], (uint64_t)s, k, &u0, &u1);
+                        const int n = (int)(u0 * 2.0), m = n + 1 + (int)(u1 * (double)(2 - n));
+                        const S2 w = sub_projected(mul(u, V), n, m);
+                        S2 wd;  // w^dagger
+                        for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) wd.a[i][j] = std::conj(w.a[j][i]);
+                        S2 h = mul2(wd, wd);
+                        const double nrm = std::sqrt(std::norm(h.a[0][0]) + std::norm(h.a[1][0]));
+                        if (!(nrm > 0.0)) { ok = false; break; }
+                        const cd al = h.a[0][0] / nrm, be = h.a[1][0] / nrm;
+                        h.a[0][0] = al; h.a[1][0] = be; h.a[0][1] = -std::conj(be); h.a[1][1] = std::conj(al);
+                        u = mul(embed(h, n, m), u);
+                    }
+                }
+                if (!ok) { failures++; continue; }
+                setU(U, L, mu, s, reunitarize(u));
+            }
+        }
+    return failures;
+}
+
+}  // extern "C"

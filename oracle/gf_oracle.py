@@ -322,3 +322,11 @@ def sexton_weingarten_trajectory(U, P, dims, terms, fast, slow, n_fast, steps, t
             fast_qpq(eps)
             update_momenta_general(P, U, dims, eps / 2, *cs)
     return H0, hamiltonian_general(U, P, dims, *ca)
+
+
+def heatbath_sweep(U, dims, beta, seed, sweep, overrelax=False):
+    """One heatbath (or overrelaxation) sweep of the Wilson action in place; raises when a site update fails."""
+    n = lib().orc_heatbath_sweep(_dp(U), _dims(dims), ctypes.c_double(beta), ctypes.c_uint64(seed), ctypes.c_uint64(sweep), ctypes.c_int(1 if overrelax else 0))
+    if n:
+        raise RuntimeError("heatbath failed at %d site(s)" % n)
+    return U

@@ -196,6 +196,24 @@ def test_random_fields_are_decomposition_independent(backend2, backend):
     assert np.array_equal(pa, pb)
 
 
+def test_heatbath_is_decomposition_independent(backend2, backend, oracle):
+    """Streams are keyed by the global site and the sweep refreshes the slab halos between colours: 1 and 2 slabs agree bitwise
+    (the reference's contract for its site-RNG kernels, src/heatbath/heatbathmodule.jl:1624-1632)."""
+    import gfb200
+
+    dims = (4, 6, 4, 8)
+    Uh = oracle.hot_start_philox(dims, 12)
+    outs = []
+    for b in (backend, backend2):
+        U = gfb200.gauge_configuration(dims, backend=b).upload(Uh)
+        h = gfb200.Heatbath(U, 5.9, seed=77)
+        gfb200.heatbath_(U, h)
+        gfb200.overrelaxation_(U, h)
+        gfb200.heatbath_(U, h)
+        outs.append(U.to_host().copy())
+    assert np.array_equal(outs[0], outs[1])
+
+
 def test_slab_constraints(backend2):
     import gfb200
 
