@@ -224,6 +224,35 @@ def cpu_steps_per_s(workload, dims_global, beta, tau, steps, warmup, budget_s):
     return value, dt / steps * 1e3 / scale, cb
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's host threads to the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned e2e buffers are
+    allocated: cudaHostAlloc places pages on the node of the allocating thread, and with eight ranks on a two-socket box
+    unbound ranks send half of their H2D/D2H traffic across the socket link (round 1: 15 GB/s per rank at N = 8 against
+    52 GB/s at N = 1).  Returns what it did for the JSON line; never fatal."""
+    try:
+        import pynvml as nv
+
+        nv.nvmlInit()
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:  # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return {"numa_node": None, "note": "the platform reports no NUMA affinity for %s" % bus}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"numa_node": node, "note": "no allowed CPU on that node"}
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception as e:  # noqa: BLE001
+        return {"numa_node": None, "note": repr(e)[:120]}
+
+
 def workload_name(args, dims_global, dims_local):
     what = {"md64": "SU(3) Wilson QPQ HMC", "md16": "SU(3) Wilson QPQ HMC", "flow32": "SU(3) RK3 Wilson flow (eps=%g) + clover E(t) per step" % FLOW_EPS,
             "stout48": "SU(3) QPQ HMC, Wilson action on %d-layer stout links (rho=%g)" % (STOUT_LAYERS, STOUT_RHO)}[args.workload]
@@ -330,6 +359,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import gfb200
 
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     backend = gfb200.B200Backend(ngpu=1, devices=[local_rank], distributed=(world > 1))
     K, W = args.steps, max(args.warmup, 3)
     sites_global = dims_global[0] * dims_global[1] * dims_global[2] * dims_global[3]
@@ -505,10 +535,30 @@ def main():
             t = torch.tensor([dt], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
+        # where the end-to-end time goes (one more repetition, synchronised between the phases; not part of the reported rate)
+        def phase(fn):
+            t1 = time.perf_counter()
+            fn()
+            backend.sync()
+            return (time.perf_counter() - t1) * 1e3
+
+        def up():
+            U.upload(Uh, local=True)
+            if P is not None:
+                P.upload(Ph, local=True)
+
+        def down():
+            U.to_host(Uh, local=True)
+            if P is not None:
+                P.to_host(Ph, local=True)
+
+        breakdown = {"upload_ms": phase(up), "download_ms": phase(down)}
+        barrier()
         bytes_dir = sites_local * (U_BYTES + (P_BYTES if P is not None else 0)) * world
         e2e = {"value": K / dt, "unit": unit, "h2d_bytes_per_step": bytes_dir / K, "d2h_bytes_per_step": (bytes_dir + 16) / K,
                "call": "upload fields (pinned host, reference gathered layout) -> %d steps with diagnostics -> download fields" % K,
-               "result": res}
+               "result": res, "host_binding_rank0": numa, "phases_rank0": breakdown,
+               "pcie_gbs_rank0": {k[:-3]: sites_local * (U_BYTES + (P_BYTES if P is not None else 0)) / (v * 1e-3) / 1e9 for k, v in breakdown.items()}}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

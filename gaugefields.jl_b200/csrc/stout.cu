@@ -20,23 +20,47 @@
 
 namespace gfb {
 
-static __constant__ double c_inv_n[40] = {
-    0.0,      1.0 / 1,  1.0 / 2,  1.0 / 3,  1.0 / 4,  1.0 / 5,  1.0 / 6,  1.0 / 7,  1.0 / 8,  1.0 / 9,  1.0 / 10, 1.0 / 11, 1.0 / 12, 1.0 / 13,
-    1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21, 1.0 / 22, 1.0 / 23, 1.0 / 24, 1.0 / 25, 1.0 / 26, 1.0 / 27,
-    1.0 / 28, 1.0 / 29, 1.0 / 30, 1.0 / 31, 1.0 / 32, 1.0 / 33, 1.0 / 34, 1.0 / 35, 1.0 / 36, 1.0 / 37, 1.0 / 38, 1.0 / 39};
-
 struct C3 {
     double2 v0, v1, v2;
 };
-__device__ __forceinline__ double2 cscale_i(double2 a, double s) { return make_double2(-a.y * s, a.x * s); }  // i*s*a
 
 // Pull-back of the exponential, L with tr(L dQ) = tr(C d exp(Q)) for Q = i*H, H Hermitian traceless given by its
 // 8 coefficients (the tape of the forward pass).  With exp(iH) = f0 + f1 H + f2 H^2 (Cayley-Hamilton, c0 = det H,
 // c1 = tr H^2 / 2) one has (Morningstar-Peardon; the reference's closed form, src/smearing/stout_fast.jl:1046-1081)
 //   i L = tr(C B1) H + tr(C B2) H^2 + f1 C + f2 (H C + C H),   B1 = sum_j (df_j/dc1) H^j,  B2 = sum_j (df_j/dc0) H^j.
 // Instead of the reference's trigonometric b_ij (singular for w -> 0 and 9u^2 = w^2, src/AbstractGaugefields.jl:3302-3343)
-// f_j and both derivative sets come from forward-mode differentiation of the nested Taylor polynomial
-//   P <- 1 + (i H / n) P,  reduced with H^3 = c1 H + c0 -- a polynomial in (c0, c1), regular everywhere.
+// f_j and both derivative sets come from forward-mode differentiation of the Horner recursion of the Taylor polynomial
+// reduced with H^3 = c1 H + c0 -- a polynomial in (c0, c1), regular everywhere (pb_terms below).
+// one Horner term of f(H) = sum_n a_n H^n (a_n = i^n / n!) and of its derivatives, reduced with H^3 = c1 H + c0:
+//   p <- a_n + H p :  (p0, p1, p2) <- (a_n + c0 p2, p0 + c1 p2, p1)
+//   d = dp/dc0     :  (d0, d1, d2) <- (p2 + c0 d2, d0 + c1 d2, d1)
+//   e = dp/dc1     :  (e0, e1, e2) <- (c0 e2, e0 + p2 + c1 e2, e1)
+// c0, c1 are real, so real and imaginary parts never mix: 14 FP64 instructions per term (the first version iterated
+// P <- 1 + (iH/n) P with complex scalings from a constant table: 33 per term plus the loop; same truncated series).
+template <int n>
+__device__ __forceinline__ void pb_terms(double c0, double c1, C3& p, C3& d, C3& e) {
+    constexpr double a = ((n & 2) ? -1.0 : 1.0) * InvFactorial<n>::v;
+    C3 np, nd, ne;
+    if ((n & 1) == 0) { np.v0.x = fma(c0, p.v2.x, a); np.v0.y = c0 * p.v2.y; }
+    else { np.v0.x = c0 * p.v2.x; np.v0.y = fma(c0, p.v2.y, a); }
+    np.v1 = make_double2(fma(c1, p.v2.x, p.v0.x), fma(c1, p.v2.y, p.v0.y));
+    np.v2 = p.v1;
+    nd.v0 = make_double2(fma(c0, d.v2.x, p.v2.x), fma(c0, d.v2.y, p.v2.y));
+    nd.v1 = make_double2(fma(c1, d.v2.x, d.v0.x), fma(c1, d.v2.y, d.v0.y));
+    nd.v2 = d.v1;
+    ne.v0 = make_double2(c0 * e.v2.x, c0 * e.v2.y);
+    ne.v1 = make_double2(fma(c1, e.v2.x, e.v0.x + p.v2.x), fma(c1, e.v2.y, e.v0.y + p.v2.y));
+    ne.v2 = e.v1;
+    p = np; d = nd; e = ne;
+    if constexpr (n > 0) pb_terms<n - 1>(c0, c1, p, d, e);
+}
+template <int N>
+__device__ __forceinline__ void pb_series(double c0, double c1, C3& p, C3& d, C3& e) {
+    const double2 z = make_double2(0.0, 0.0);
+    p = {z, z, z}; d = {z, z, z}; e = {z, z, z};
+    pb_terms<N>(c0, c1, p, d, e);
+}
+
 __device__ __forceinline__ M3 exp_pullback(const M3& cm, const double* q) {
     const H3 h = h3_from_coeffs(q, 1.0);
     const double a01 = h.o01.x * h.o01.x + h.o01.y * h.o01.y;
@@ -45,30 +69,12 @@ __device__ __forceinline__ M3 exp_pullback(const M3& cm, const double* q) {
     const double c1 = 0.5 * (h.d0 * h.d0 + h.d1 * h.d1 + h.d2 * h.d2) + a01 + a02 + a12;
     const double2 t3 = cmul(h.o01, h.o12);
     const double c0 = h.d0 * h.d1 * h.d2 + 2.0 * (t3.x * h.o02.x + t3.y * h.o02.y) - h.d0 * a12 - h.d1 * a02 - h.d2 * a01;
-    // |eigenvalues| <= sqrt(4 c1 / 3): 21 terms reach 1e-21 for c1 <= 0.75, 39 terms for c1 <= 12
-    const int N = (c1 <= 0.75) ? 21 : 39;
-    C3 p = {make_double2(1.0, 0.0), make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
-    C3 d0 = {make_double2(0.0, 0.0), make_double2(0.0, 0.0), make_double2(0.0, 0.0)};  // d/dc0
-    C3 d1 = d0;                                                                          // d/dc1
-    for (int n = N; n >= 1; n--) {
-        const double s = c_inv_n[n];
-        // H*P = c0 p2 + (p0 + c1 p2) H + p1 H^2
-        C3 np, nd0, nd1;
-        np.v0 = make_double2(c0 * p.v2.x, c0 * p.v2.y);
-        np.v1 = make_double2(fma(c1, p.v2.x, p.v0.x), fma(c1, p.v2.y, p.v0.y));
-        np.v2 = p.v1;
-        nd0.v0 = make_double2(fma(c0, d0.v2.x, p.v2.x), fma(c0, d0.v2.y, p.v2.y));
-        nd0.v1 = make_double2(fma(c1, d0.v2.x, d0.v0.x), fma(c1, d0.v2.y, d0.v0.y));
-        nd0.v2 = d0.v1;
-        nd1.v0 = make_double2(c0 * d1.v2.x, c0 * d1.v2.y);
-        nd1.v1 = make_double2(fma(c1, d1.v2.x, d1.v0.x) + p.v2.x, fma(c1, d1.v2.y, d1.v0.y) + p.v2.y);
-        nd1.v2 = d1.v1;
-        p.v0 = cscale_i(np.v0, s); p.v0.x += 1.0;
-        p.v1 = cscale_i(np.v1, s);
-        p.v2 = cscale_i(np.v2, s);
-        d0.v0 = cscale_i(nd0.v0, s); d0.v1 = cscale_i(nd0.v1, s); d0.v2 = cscale_i(nd0.v2, s);
-        d1.v0 = cscale_i(nd1.v0, s); d1.v1 = cscale_i(nd1.v1, s); d1.v2 = cscale_i(nd1.v2, s);
-    }
+    // |eigenvalues| x <= sqrt(4 c1 / 3); the derivative series lose one power: remainder ~ x^N / N!.
+    //   c1 <= 3/64 (x <= 1/4): N = 14 -> 4e-20;  c1 <= 3/4 (x <= 1): N = 21 -> 2e-20;  c1 <= 12 (x <= 4): N = 39 -> 1e-23 * 4^39 = 1.5e-23..
+    C3 p, d0, d1;  // f_j, df_j/dc0, df_j/dc1
+    if (c1 <= 0.046875) pb_series<14>(c0, c1, p, d0, d1);
+    else if (c1 <= 0.75) pb_series<21>(c0, c1, p, d0, d1);
+    else pb_series<39>(c0, c1, p, d0, d1);
     // H and H^2 as full matrices
     M3 hm, h2;
     hm.e[0] = make_double2(h.d0, 0.0); hm.e[4] = make_double2(h.d1, 0.0); hm.e[8] = make_double2(h.d2, 0.0);

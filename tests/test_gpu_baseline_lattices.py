@@ -92,3 +92,46 @@ def test_32x4_flow_energy_against_oracle(backend, oracle):
     assert np.abs(U.to_host() - Uh).max() < 1e-12
     e, want = gfb200.energy_density(U), oracle.energy_density_clover(Uh, dims)
     assert abs(e - want) < 1e-11 * max(1.0, abs(want))
+
+
+def test_64x4_size_independent_properties(backend):
+    """BASELINE.json's full size (64^4, the bench lattice; the oracle cannot reach it): cold-start invariants
+    (test/md_driver.jl:371-395 in the reference), MD reversibility (test/md_driver.jl:417-482) and the flow's monotone energy,
+    all evaluated on the device through the primitive table (no 10 GB host copies)."""
+    import gfb200
+
+    dims = (64, 64, 64, 64)
+    V = 64 ** 4
+    U = gfb200.gauge_configuration(dims, backend=backend)  # cold
+    assert gfb200.calculate_Plaquette(U) == 18.0 * V
+    P = gfb200.gauge_momenta(U)
+    action = _action(gfb200, U, 6.2)
+    md = gfb200.md_driver(U, action, steps=2, trajectory_length=0.1, integrator=gfb200.QPQ, fused=True)
+    res = gfb200.md_trajectory_(U, P, md)  # cold links, zero momenta: nothing moves
+    assert res.delta_hamiltonian == 0.0 and P.dot() == 0.0 and gfb200.calculate_Plaquette(U) == 18.0 * V
+    del U
+    U = gfb200.gauge_configuration(dims, backend=backend, start="hot", seed=1234)
+    U0 = gfb200.copy_configuration(U)
+    P = gfb200.gaussian_momenta(U, seed=0x5678, sweep=0)
+    k0 = P.dot()
+    assert abs(k0 / (32.0 * V) - 1.0) < 2e-3  # 32 N(0,1) coefficients per site
+    md = gfb200.md_driver(U, action, steps=4, trajectory_length=0.2, integrator=gfb200.QPQ, fused=True)
+    r1 = gfb200.md_trajectory_(U, P, md)
+    P.add_(-2.0, P)  # P <- -P
+    r2 = gfb200.md_trajectory_(U, P, md)
+    assert abs(r1.delta_hamiltonian + r2.delta_hamiltonian) < 1e-7 * abs(r1.initial_hamiltonian)
+    assert abs(P.dot() - k0) < 1e-10 * k0
+    diff = gfb200.link_field(U, 0).similar()
+    sq = diff.similar()
+    worst = 0.0
+    for mu in range(4):
+        gfb200.substitute_U_(diff, gfb200.link_field(U, mu))
+        gfb200.add_U_(diff, -1.0, gfb200.link_field(U0, mu))
+        gfb200.mul_(sq, diff, diff.H)
+        worst = max(worst, gfb200.tr(sq).real)
+    # root-mean-square difference per matrix entry of U_mu - U0_mu over 16.7 M sites (reference bar on the maximum: 2e-12)
+    rms = (worst / (9.0 * V)) ** 0.5
+    assert rms < 2e-13, rms
+    e0 = gfb200.energy_density(U)
+    gfb200.flow_(U, gfb200.gradient_flow(U, steps=1, step_size=0.01))
+    assert gfb200.energy_density(U) < e0
