@@ -157,6 +157,9 @@ struct TmArgs {
     unsigned swz;
     double2* peer_prev;  // previous slab's output buffer: our slice 0 (spatial links) goes to its slot tloc
     double2* peer_next;  // next slab's output buffer: our slice tloc-1 (all links) goes to its slot tloc+1
+    // round barrier of the persistent grid (nullptr: off): every CTA's producer arrives once per round (= its k-th item) and
+    // starts the copies of round k+1 only when all CTAs have arrived k+1 times; zeroed by the host before the launch
+    unsigned long long* round_ctr;
 };
 
 // item -> (tile origin, t-segment)
@@ -458,13 +461,32 @@ template <int N>
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(N)); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 
-__device__ __noinline__ void tm_producer(const TmMaps& maps, const Geom& g, const TmPlan& pl, unsigned char* smem, uint64_t* bars) {
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __noinline__ void tm_producer(const TmMaps& maps, const Geom& g, const TmPlan& pl, unsigned char* smem, uint64_t* bars,
+                                         unsigned long long* round_ctr) {
     unsigned char* const sS = smem;
     unsigned char* const sR = smem + tm::S_RING * tm::S_SLOT;
     unsigned ephase = ~0u;  // EMPTY barriers start "released": the first wait on each passes (parity of the preceding phase)
     const bool leader = elect_one();
     const long nitems = (long)pl.ntiles * pl.nseg;
-    for (long item = blockIdx.x; item < nitems; item += gridDim.x) {
+    // Round barrier (persistent grid, one CTA per SM, all co-resident).  Without it nothing keeps the 148 marches aligned: a
+    // CTA that is 1 % faster is 17 slices ahead after the 27 rounds x 64 slices of a 64^4 pass, its neighbours' halo links
+    // have left L2 by the time it asks for them, and they are read from DRAM again (2644 instead of 1664 B/site,
+    // profiles/r2_tmarch.md).  With it all CTAs start a round together and drift only within one march.
+    long round = 0;
+    for (long item = blockIdx.x; item < nitems; item += gridDim.x, round++) {
+        if (round_ctr != nullptr && round > 0) {
+            if (leader) {
+                const unsigned long long want = (unsigned long long)round * gridDim.x;
+                while (ld_acquire_gpu(round_ctr) < want) __nanosleep(200);
+            }
+            __syncwarp();
+        }
         const TmItem it = decode_item(pl, item);
         // every box of one part of the slice in storage slot `tslot` into ring slot `ring`, once the consumers released it
         auto fill = [&](int is_r, int tslot, int ring) {
@@ -495,10 +517,14 @@ __device__ __noinline__ void tm_producer(const TmMaps& maps, const Geom& g, cons
             fill(0, t_up(t + 1), rs2);
             rs = rs1;
         }
+        // all copies of this item are issued (the link warps are at most one slice behind)
+        if (round_ctr != nullptr && leader) atomicAdd(round_ctr, 1ull);
     }
+    // CTAs that have no item in the last round still arrive for it
+    if (round_ctr != nullptr && leader && round * (long)gridDim.x < nitems) atomicAdd(round_ctr, 1ull);
 }
 
-template <bool READ_Z, bool WRITE_Z, bool DO_EXP, bool SPLIT = false>
+template <bool READ_Z, bool WRITE_Z, bool DO_EXP>
 __device__ __forceinline__ void tm_consumer(const int MU, const Geom& g, const TmPlan& pl, const TmArgs& ar, unsigned char* smem, uint64_t* bars,
                                             const tm::Tables* __restrict__ tab) {
     const int tid = threadIdx.x;
@@ -538,7 +564,7 @@ __device__ __forceinline__ void tm_consumer(const int MU, const Geom& g, const T
             const unsigned d_r = smem_u32(sR + (j & 1) * tm::R_SLOT) - sc;
             const unsigned d_n = smem_u32(sS + rs1 * tm::S_SLOT) - sc;
             const bool last = j + 1 == it.len;
-            tm_step<READ_Z, WRITE_Z, DO_EXP && !SPLIT>(MU, g, ar, od, t, s3, sc, d_r, d_n, G, [&] {
+            tm_step<READ_Z, WRITE_Z, DO_EXP>(MU, g, ar, od, t, s3, sc, d_r, d_n, G, [&] {
                 // this warp is done with slice t's S and R parts (the S part of slice t+1 stays for the next step, unless this
                 // was the last step of the segment)
                 __syncwarp();
@@ -548,8 +574,6 @@ __device__ __forceinline__ void tm_consumer(const int MU, const Geom& g, const T
                     if (last) mbar_arrive(bars + kNBars + rs1);
                 }
             });
-            // Z' of slice t is in global memory: every lane releases its own eight stores to the drift warp that exponentiates
-            if (SPLIT) mbar_arrive(bars + 2 * kNBars + (tid >> 5));
             rs = rs1;
         }
     }
@@ -568,143 +592,12 @@ k_tmarch_ws(const __grid_constant__ TmMaps maps, const tm::Tables* __restrict__ 
     __syncthreads();
     if (threadIdx.x >= tm::NTHREADS) {
         reg_dec<GFB_TM_PREGS>();
-        if (threadIdx.x < tm::NTHREADS + 32) tm_producer(maps, g, pl, smem, bars);
+        if (threadIdx.x < tm::NTHREADS + 32) tm_producer(maps, g, pl, smem, bars, ar.round_ctr);
         return;
     }
     reg_inc<((64512 - 128 * GFB_TM_PREGS) / 256) & ~7>();
     const int mu = threadIdx.x / tm::SITES;  // warp-uniform: two warps per direction
     tm_consumer<READ_Z, WRITE_Z, DO_EXP>(mu, g, pl, ar, smem, bars, tab);
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Variant C (GFB200_TMARCH_WS=2, passes that write Z' and exponentiate): three roles.  Warps 0-7 compute staples, TA force and
-// Z' (as variant B with DO_EXP off) and hand Z' over through global memory (their own stores, released on one mbarrier per link
-// warp); warps 8-11 ("drift warps", two links per thread) read Z' back from L2 and the link from the tile in shared memory and
-// compute U' = exp(c Z') U; warps 12-15 are the producer group.  Why: with two warps per scheduler running the same instruction
-// stream the FP64 pipe idles whenever both are in a load cluster or at a step start (profiles/r2_tmarch.md: 60 % pipe
-// utilisation, the kernel's only limiter); a third warp per scheduler needs <= 168 registers per link thread, which the staple
-// pipeline cannot do -- but the exponential (a quarter of the FP64 work) needs no staple state at all, so it moves to a third,
-// light warp per scheduler with a different instruction stream.  Registers: 256 x 192 + 128 x 104 + 128 x 24 = 65536.
-// ---------------------------------------------------------------------------------------------------------------------
-constexpr int kWs3Threads = tm::NTHREADS + 256;
-constexpr int kLinkWarps = tm::NTHREADS / 32, kDriftWarps = 4;
-#ifndef GFB_TM_LREGS
-#define GFB_TM_LREGS 192
-#endif
-#ifndef GFB_TM_DREGS
-#define GFB_TM_DREGS 104
-#endif
-static_assert(256 * GFB_TM_LREGS + 128 * GFB_TM_DREGS + 128 * 24 <= 65536, "register file");
-
-__device__ __forceinline__ double ld_cta(const double* p) {
-    double v;
-    asm volatile("ld.relaxed.cta.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__device__ __forceinline__ void tm_drift(const Geom& g, const TmPlan& pl, const TmArgs& ar, unsigned char* smem, uint64_t* bars,
-                                         const tm::Tables* __restrict__ tab) {
-    const int lane = threadIdx.x & 31, e = (threadIdx.x >> 5) & (kDriftWarps - 1);
-    unsigned char* const sS = smem;
-    unsigned char* const sR = smem + tm::S_RING * tm::S_SLOT;
-    // the two links of this thread: lane `lane` of link warps e and e + 4
-    int od0[2], mu[2], sx[2], sy[2], sz[2];
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const int ltid = (e + kDriftWarps * h) * 32 + lane;
-        const int sidx = ltid & (tm::SITES - 1);
-        od0[h] = tab->desc[0][ltid];
-        mu[h] = ltid / tm::SITES;
-        sx[h] = sidx & (tm::BX - 1); sy[h] = (sidx / tm::BX) & (tm::BY - 1); sz[h] = sidx / (tm::BX * tm::BY);
-    }
-    unsigned fphase = 0, zphase = 0;
-    auto wait_full = [&](int s) {
-        mbar_wait(bars + s, (fphase >> s) & 1u);
-        fphase ^= 1u << s;
-    };
-    const long nitems = (long)pl.ntiles * pl.nseg;
-    for (long item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const TmItem it = decode_item(pl, item);
-        unsigned s3[2];
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            Coord x;
-            x.x = it.x0 + sx[h]; x.y = it.y0 + sy[h]; x.z = it.z0 + sz[h]; x.t = it.tb;
-            s3[h] = (unsigned)s3_of(g, x);
-        }
-        // the same FULL-barrier sequence as the link warps (the tile's own links are read from the ring slots)
-        wait_full(0);
-        wait_full(tm::S_RING + 0);
-        wait_full(1);
-        int rs = 0;
-        for (int j = 0; j < it.len; j++) {
-            const int t = it.tb + j;
-            const int rs1 = (rs == 2) ? 0 : rs + 1;
-            if (j > 0) {
-                wait_full(tm::S_RING + (j & 1));
-                wait_full(rs1);
-            }
-            const unsigned sc = smem_u32(sS + rs * tm::S_SLOT);
-            const unsigned d_r = smem_u32(sR + (j & 1) * tm::R_SLOT) - sc;
-            const unsigned d_n = smem_u32(sS + rs1 * tm::S_SLOT) - sc;
-            const bool last = j + 1 == it.len;
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int w = e + kDriftWarps * h;
-                mbar_wait(bars + 2 * kNBars + w, (zphase >> w) & 1u);  // Z' of slice t from link warp w
-                zphase ^= 1u << w;
-                const unsigned zo = (unsigned)(t * 32 + mu[h] * 8) * (unsigned)g.v3 + s3[h];
-                const unsigned zsb = (unsigned)g.v3 * 8u;
-                double f[8];
-#pragma unroll
-                for (int k = 0; k < 8; k++) f[k] = ld_cta(reinterpret_cast<const double*>(reinterpret_cast<const char*>(ar.zout + zo) + (size_t)k * zsb));
-                const M3 U = lds_m3(sm_operand(od0[h], sc, d_r, d_n, ar.swz));
-                if (h == 1) {  // both links of slice t are in registers: the slots may be refilled
-                    __syncwarp();
-                    if (lane == 0) {
-                        mbar_arrive(bars + kNBars + rs);
-                        mbar_arrive(bars + kNBars + tm::S_RING + (j & 1));
-                        if (last) mbar_arrive(bars + kNBars + rs1);
-                    }
-                }
-                const M3 r = exp_ta_times_su3(f, ar.c, U);
-                const unsigned uo = (unsigned)(t * 36 + mu[h] * 9) * (unsigned)g.v3 + s3[h];
-                m3_store(ar.uout + uo, (unsigned)g.v3, r);
-                if (ar.peer_prev != nullptr && t == 0 && mu[h] < 3)
-                    m3_store(ar.peer_prev + ((unsigned)(g.tloc * 36 + mu[h] * 9) * (unsigned)g.v3 + s3[h]), (unsigned)g.v3, r);
-                if (ar.peer_next != nullptr && t == g.tloc - 1)
-                    m3_store(ar.peer_next + ((unsigned)((g.tloc + 1) * 36 + mu[h] * 9) * (unsigned)g.v3 + s3[h]), (unsigned)g.v3, r);
-            }
-            rs = rs1;
-        }
-    }
-}
-
-template <bool READ_Z>
-__global__ void __launch_bounds__(kWs3Threads, 1)
-k_tmarch_ws3(const __grid_constant__ TmMaps maps, const tm::Tables* __restrict__ tab, Geom g, TmPlan pl, TmArgs ar) {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + tm::BAR_OFF);
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < kNBars; i++) mbar_init(bars + i, 1);
-        for (int i = 0; i < kNBars; i++) mbar_init(bars + kNBars + i, kLinkWarps + kDriftWarps);
-        for (int i = 0; i < kLinkWarps; i++) mbar_init(bars + 2 * kNBars + i, 32);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x >= tm::NTHREADS + 128) {
-        reg_dec<24>();
-        if (threadIdx.x < tm::NTHREADS + 128 + 32) tm_producer(maps, g, pl, smem, bars);
-        return;
-    }
-    if (threadIdx.x >= tm::NTHREADS) {
-        reg_dec<GFB_TM_DREGS>();
-        tm_drift(g, pl, ar, smem, bars, tab);
-        return;
-    }
-    reg_inc<GFB_TM_LREGS>();
-    const int mu = threadIdx.x / tm::SITES;  // warp-uniform: two warps per direction
-    tm_consumer<READ_Z, true, true, true>(mu, g, pl, ar, smem, bars, tab);
 }
 
 constexpr size_t kTmSmem = tm::SMEM_DATA;  // 232448 = the opt-in maximum; the mbarriers live in the tail of R slot 0
@@ -752,6 +645,20 @@ const tm::Tables* device_tables(int dev) {
     if (cudaMemcpy(d, &host, sizeof(tm::Tables), cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); cudaFree(d); return nullptr; }
     if (cudaMemcpyToSymbol(c_tm_box, host.box, sizeof(host.box)) != cudaSuccess) { cudaGetLastError(); cudaFree(d); return nullptr; }
     per_dev[dev & 63] = d;
+    return d;
+}
+
+// round-barrier counter of a persistent launch, one per (device, stream): launches on one stream are serialised
+unsigned long long* round_counter_for(int dev, cudaStream_t st) {
+    static std::mutex mtx;
+    static std::unordered_map<unsigned long long, unsigned long long*> per;
+    std::lock_guard<std::mutex> lock(mtx);
+    const unsigned long long key = ((unsigned long long)(uintptr_t)st << 6) ^ (unsigned long long)(dev & 63);
+    auto it = per.find(key);
+    if (it != per.end()) return it->second;
+    unsigned long long* d = nullptr;
+    if (cudaMalloc(&d, sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    per.emplace(key, d);
     return d;
 }
 
@@ -850,6 +757,15 @@ bool launch_tmarch_fused(cudaStream_t st, const Geom& g, int t_begin, int t_coun
     ar.swz = swizzle ? 0x70u : 0u;
     ar.peer_prev = fa.do_exp ? fa.peer_prev : nullptr;
     ar.peer_next = fa.do_exp ? fa.peer_next : nullptr;
+    // round barrier: persistent launches of the warp-specialised kernel with at least two full rounds of long marches.  Measured
+    // (profiles/r2_tmarch.md): 64^4 (28 rounds x 64 slices) DRAM read 1880 -> 1097 B/site, 10.29 -> 9.83 ms; 32^4 (7 rounds x 16
+    // slices, no re-read problem) 0.619 -> 0.625 ms, hence the length threshold.  GFB200_TMARCH_ROUNDSYNC=0 / 2: off / always.
+    ar.round_ctr = nullptr;
+    const int rsync = env_int("GFB200_TMARCH_ROUNDSYNC", 1);
+    if (ws && grid == (unsigned)nsm && nitems >= 2L * nsm && rsync && (pl.seg_len >= 32 || rsync == 2)) {
+        ar.round_ctr = round_counter_for(dev, st);
+        if (ar.round_ctr && cudaMemsetAsync(ar.round_ctr, 0, sizeof(unsigned long long), st) != cudaSuccess) { cudaGetLastError(); ar.round_ctr = nullptr; }
+    }
 #define GFB_LAUNCH_TM(R, W, E)                                                                                                 \
     do {                                                                                                                        \
         static bool attr_set[2][64] = {};  /* per device: one process may drive several GPUs */                                 \
@@ -875,19 +791,6 @@ bool launch_tmarch_fused(cudaStream_t st, const Geom& g, int t_begin, int t_coun
             kern<<<grid, tm::NTHREADS, kTmSmem, st>>>(maps, tab, g, pl, ar);                                                    \
         }                                                                                                                       \
     } while (0)
-    if (ws && env_int("GFB200_TMARCH_WS", 1) == 2 && fa.do_exp && (fa.read_z || fa.write_z)) {
-        static bool attr3[2][64] = {};
-        for (int r = 0; r < 2; r++) {
-            if (attr3[r][dev & 63]) continue;
-            const cudaError_t e = r ? cudaFuncSetAttribute(k_tmarch_ws3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmSmem)
-                                    : cudaFuncSetAttribute(k_tmarch_ws3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmSmem);
-            if (e != cudaSuccess) { cudaGetLastError(); return false; }
-            attr3[r][dev & 63] = true;
-        }
-        if (fa.read_z) k_tmarch_ws3<true><<<grid, kWs3Threads, kTmSmem, st>>>(maps, tab, g, pl, ar);
-        else k_tmarch_ws3<false><<<grid, kWs3Threads, kTmSmem, st>>>(maps, tab, g, pl, ar);
-        return true;
-    }
     if (fa.read_z) {
         if (fa.do_exp) GFB_LAUNCH_TM(true, true, true);
         else GFB_LAUNCH_TM(true, true, false);
