@@ -569,6 +569,15 @@ def main():
         parity = parity_check(gfb200, backend, world, dist, torch)
 
     if rank == 0:
+        if is_md and not args.unfused and kern_ms and clocks and clocks.get("sm_mhz"):
+            # The fused pass is bound by FP64 issue, not by HBM: 1506 FP64 warp instructions per link and launch
+            # (ncu, profiles/r2_ncu_tmarch_ws_64x4.csv: 197.4 M per 32^4 pass) against one FP64 warp instruction per 2 cycles per SM
+            # sub-partition (148 SMs x 4).  Informative: the contract's roofline above stays the HBM one.
+            fp64_instr = 1506.0 * 4.0 * sites_local / 32.0
+            fp64_peak = 148 * 4 * clocks["sm_mhz"] * 1e6 / 2.0
+            extra = dict(extra, fp64_pipe={"warp_instructions_per_launch": fp64_instr, "peak_warp_instructions_per_s": fp64_peak,
+                                           "frac": fp64_instr / (kern_ms * 1e-3) / fp64_peak,
+                                           "hbm_frac_at_full_fp64_pipe": (kern_bytes * sites_local / (fp64_instr / fp64_peak)) / 1e9 / peak})
         line = {
             "metric": metric, "value": K / (ms * 1e-3), "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",

@@ -99,9 +99,15 @@ __device__ __forceinline__ M3 exp_pullback(const M3& cm, const double* q) {
     return r;
 }
 
+#ifndef GFB_STOUT_LOCAL_MINB
+#define GFB_STOUT_LOCAL_MINB 3  // 168 registers, 308 bytes of spills in L1: back_prop 61.1 -> 60.0 ms at 48^3x96 (the gather is slower at 3)
+#endif
+#ifndef GFB_STOUT_GATHER_MINB
+#define GFB_STOUT_GATHER_MINB 2
+#endif
 // kernel 1: site-local part of the pull-back and Lambda = dS/dC
 template <bool FULL3>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(128, GFB_STOUT_LOCAL_MINB)
 k_stout_local(Geom g, const double2* __restrict__ u, const double2* __restrict__ dout, double2* __restrict__ lambda, double2* __restrict__ din, double rho) {
     const int mu = threadIdx.y;
     const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -146,7 +152,7 @@ k_stout_local(Geom g, const double2* __restrict__ u, const double2* __restrict__
 // (e) U_b(y-b+a)^dag U_a(y-b)^dag L_b(y-b)^dag  U_alpha(x+beta) in the adjoint upper staple of C_beta(x)^dag, x = y-beta
 // (d) L_b(y+a-b) U_a(y-b)^dag U_b(y-b)        U_alpha(x-beta+alpha)... in the lower staple of C_beta(x), x = y+alpha-beta
 // (a = alpha, b = beta, L = Lambda).  Pairs sharing a factor are combined: 10 products per beta.
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(128, GFB_STOUT_GATHER_MINB)
 k_stout_gather(Geom g, const double2* __restrict__ u, const double2* __restrict__ lambda, double2* __restrict__ din, double rho) {
     const int al = threadIdx.y;
     const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -53,6 +53,12 @@ struct TmPlan {
     // at the same time (L2 hits); with the plain x,y,z order a wave of 148 tiles at 64^3 is one z-layer of tiles whose z-halos
     // were loaded a whole wave (hundreds of MB) earlier: 2783 B/site of DRAM traffic instead of 1664 (profiles/r2_tmarch.md)
     int by, bz;
+    // Staggered start (peer-store slabs with short marches): CTA b first marches slices [s_b, t_count) of its first tile and
+    // finishes with that tile's slices [0, s_b), s_b = b * stagger / gridDim.  Without it all CTAs run in lockstep (they start
+    // together and nothing desynchronises 28 rounds of 8 slices), so the whole grid stores its slice-0 / slice-(tloc-1) links
+    // to the neighbours' halo slots in the SAME step: 5.4 MB in 5.7 us = 0.96 TB/s, more than NVLink takes, while the link is
+    // idle in the other six steps.  Work conserving: one extra segment start per CTA, no idle time.  0 = off.
+    int stagger;
 };
 
 
@@ -186,6 +192,24 @@ __device__ __forceinline__ SmOp sm_operand(int d, unsigned sc, unsigned d_r, uns
     o.p ^= (o.p >> 3) & ((((unsigned)d >> 30) & 1u) * swz);  // 128-byte swizzle of the tile boxes (tmarch_geom.h, lookup())
     o.stride = (((unsigned)d >> 16) & 0xFFu) * 16u;
     return o;
+}
+
+// k-th work item of this CTA in a persistent launch (static assignment: items b, b + G, b + 2G, ...; see TmPlan::stagger)
+__device__ __forceinline__ bool seq_item(const TmPlan& pl, long k, TmItem* it) {
+    const long nitems = (long)pl.ntiles * pl.nseg, G = gridDim.x, b = blockIdx.x;
+    const long n = b < nitems ? (nitems - b + G - 1) / G : 0;
+    const int s = pl.stagger ? (int)(b * pl.stagger / G) : 0;
+    if (k < n) {
+        *it = decode_item(pl, b + k * G);
+        if (k == 0 && s > 0) { it->tb += s; it->len -= s; }
+        return true;
+    }
+    if (k == n && n > 0 && s > 0) {
+        *it = decode_item(pl, b);
+        it->len = s;
+        return true;
+    }
+    return false;
 }
 
 // One slice step of one link-thread: the six staples from shared memory (the backward-t staple G is carried), the TA force,
@@ -479,7 +503,8 @@ __device__ __noinline__ void tm_producer(const TmMaps& maps, const Geom& g, cons
     // have left L2 by the time it asks for them, and they are read from DRAM again (2644 instead of 1664 B/site,
     // profiles/r2_tmarch.md).  With it all CTAs start a round together and drift only within one march.
     long round = 0;
-    for (long item = blockIdx.x; item < nitems; item += gridDim.x, round++) {
+    TmItem it;
+    for (; seq_item(pl, round, &it); round++) {
         if (round_ctr != nullptr && round > 0) {
             if (leader) {
                 const unsigned long long want = (unsigned long long)round * gridDim.x;
@@ -487,7 +512,6 @@ __device__ __noinline__ void tm_producer(const TmMaps& maps, const Geom& g, cons
             }
             __syncwarp();
         }
-        const TmItem it = decode_item(pl, item);
         // every box of one part of the slice in storage slot `tslot` into ring slot `ring`, once the consumers released it
         auto fill = [&](int is_r, int tslot, int ring) {
             const int s = is_r ? tm::S_RING + ring : ring;
@@ -541,9 +565,8 @@ __device__ __forceinline__ void tm_consumer(const int MU, const Geom& g, const T
         fphase ^= 1u << s;
     };
     const bool lane0 = (tid & 31) == 0;
-    const long nitems = (long)pl.ntiles * pl.nseg;
-    for (long item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const TmItem it = decode_item(pl, item);
+    TmItem it;
+    for (long k = 0; seq_item(pl, k, &it); k++) {
         Coord x;
         x.x = it.x0 + sx; x.y = it.y0 + sy; x.z = it.z0 + sz; x.t = it.tb;
         const unsigned s3 = (unsigned)s3_of(g, x);
@@ -628,6 +651,7 @@ TmPlan make_plan(const Geom& g, int t_begin, int t_count, int nsm) {
     int bz = (int)(per_x / by + 0.5);
     bz = bz < 1 ? 1 : (bz > pl.ntz ? pl.ntz : bz);
     pl.by = by; pl.bz = bz;
+    pl.stagger = 0;
     return pl;
 }
 
@@ -766,6 +790,14 @@ bool launch_tmarch_fused(cudaStream_t st, const Geom& g, int t_begin, int t_coun
         ar.round_ctr = round_counter_for(dev, st);
         if (ar.round_ctr && cudaMemsetAsync(ar.round_ctr, 0, sizeof(unsigned long long), st) != cudaSuccess) { cudaGetLastError(); ar.round_ctr = nullptr; }
     }
+    // staggered start: peer-store slabs marched in one segment by a persistent grid without the round barrier
+    // (GFB200_TMARCH_STAGGER=0: off, 2: also without peers -- test hook)
+    {
+        const int stg = env_int("GFB200_TMARCH_STAGGER", 1);
+        const bool peers = ar.peer_prev != nullptr || ar.peer_next != nullptr;
+        if (ws && stg && (peers || stg == 2) && ar.round_ctr == nullptr && grid == (unsigned)nsm && pl.nseg == 1 && t_count >= 2) pl.stagger = t_count;
+    }
+    if (env_int("GFB200_PEER_NOSTORE", 0)) ar.peer_prev = ar.peer_next = nullptr;  // timing experiments only: halos stay stale
 #define GFB_LAUNCH_TM(R, W, E)                                                                                                 \
     do {                                                                                                                        \
         static bool attr_set[2][64] = {};  /* per device: one process may drive several GPUs */                                 \
