@@ -36,6 +36,9 @@
 #ifndef GFB_TM_PREGS
 #define GFB_TM_PREGS 24  // registers per producer-group thread; the consumers get (64512 - 128*PREGS)/256 rounded down to 8
 #endif
+#ifndef GFB_TM_RSYNC_LATE
+#define GFB_TM_RSYNC_LATE 1  // round barrier after (1) or before (0) the prologue copies of the next item
+#endif
 #ifndef GFB_TM_DEBUG
 #define GFB_TM_DEBUG 0  // 1: no staple arithmetic (copies + operand reads only); 2: no global->shared copies (barriers only; arithmetic on stale smem); 3: no shared-memory reads (arithmetic on fabricated operands)
 #endif
@@ -53,12 +56,6 @@ struct TmPlan {
     // at the same time (L2 hits); with the plain x,y,z order a wave of 148 tiles at 64^3 is one z-layer of tiles whose z-halos
     // were loaded a whole wave (hundreds of MB) earlier: 2783 B/site of DRAM traffic instead of 1664 (profiles/r2_tmarch.md)
     int by, bz;
-    // Staggered start (peer-store slabs with short marches): CTA b first marches slices [s_b, t_count) of its first tile and
-    // finishes with that tile's slices [0, s_b), s_b = b * stagger / gridDim.  Without it all CTAs run in lockstep (they start
-    // together and nothing desynchronises 28 rounds of 8 slices), so the whole grid stores its slice-0 / slice-(tloc-1) links
-    // to the neighbours' halo slots in the SAME step: 5.4 MB in 5.7 us = 0.96 TB/s, more than NVLink takes, while the link is
-    // idle in the other six steps.  Work conserving: one extra segment start per CTA, no idle time.  0 = off.
-    int stagger;
 };
 
 
@@ -192,24 +189,6 @@ __device__ __forceinline__ SmOp sm_operand(int d, unsigned sc, unsigned d_r, uns
     o.p ^= (o.p >> 3) & ((((unsigned)d >> 30) & 1u) * swz);  // 128-byte swizzle of the tile boxes (tmarch_geom.h, lookup())
     o.stride = (((unsigned)d >> 16) & 0xFFu) * 16u;
     return o;
-}
-
-// k-th work item of this CTA in a persistent launch (static assignment: items b, b + G, b + 2G, ...; see TmPlan::stagger)
-__device__ __forceinline__ bool seq_item(const TmPlan& pl, long k, TmItem* it) {
-    const long nitems = (long)pl.ntiles * pl.nseg, G = gridDim.x, b = blockIdx.x;
-    const long n = b < nitems ? (nitems - b + G - 1) / G : 0;
-    const int s = pl.stagger ? (int)(b * pl.stagger / G) : 0;
-    if (k < n) {
-        *it = decode_item(pl, b + k * G);
-        if (k == 0 && s > 0) { it->tb += s; it->len -= s; }
-        return true;
-    }
-    if (k == n && n > 0 && s > 0) {
-        *it = decode_item(pl, b);
-        it->len = s;
-        return true;
-    }
-    return false;
 }
 
 // One slice step of one link-thread: the six staples from shared memory (the backward-t staple G is carried), the TA force,
@@ -503,15 +482,20 @@ __device__ __noinline__ void tm_producer(const TmMaps& maps, const Geom& g, cons
     // have left L2 by the time it asks for them, and they are read from DRAM again (2644 instead of 1664 B/site,
     // profiles/r2_tmarch.md).  With it all CTAs start a round together and drift only within one march.
     long round = 0;
-    TmItem it;
-    for (; seq_item(pl, round, &it); round++) {
-        if (round_ctr != nullptr && round > 0) {
-            if (leader) {
-                const unsigned long long want = (unsigned long long)round * gridDim.x;
-                while (ld_acquire_gpu(round_ctr) < want) __nanosleep(200);
+    for (long item = blockIdx.x; item < nitems; item += gridDim.x, round++) {
+        const TmItem it = decode_item(pl, item);
+        auto round_wait = [&]() {
+            if (round_ctr != nullptr && round > 0) {
+                if (leader) {
+                    const unsigned long long want = (unsigned long long)round * gridDim.x;
+                    while (ld_acquire_gpu(round_ctr) < want) __nanosleep(200);
+                }
+                __syncwarp();
             }
-            __syncwarp();
-        }
+        };
+#if !GFB_TM_RSYNC_LATE
+        round_wait();
+#endif
         // every box of one part of the slice in storage slot `tslot` into ring slot `ring`, once the consumers released it
         auto fill = [&](int is_r, int tslot, int ring) {
             const int s = is_r ? tm::S_RING + ring : ring;
@@ -533,6 +517,11 @@ __device__ __noinline__ void tm_producer(const TmMaps& maps, const Geom& g, cons
         fill(0, it.tb, 0);
         fill(1, it.tb, 0);
         fill(0, t_up(it.tb), 1);
+#if GFB_TM_RSYNC_LATE
+        // the barrier gates the march, not its prologue: the first slices of the next tile are requested while the slower CTAs
+        // finish their round, so a CTA resumes one slice after the barrier opens instead of one copy latency + one slice
+        round_wait();
+#endif
         int rs = 0;
         for (int j = 0; j + 1 < it.len; j++) {
             const int t = it.tb + j;
@@ -565,8 +554,9 @@ __device__ __forceinline__ void tm_consumer(const int MU, const Geom& g, const T
         fphase ^= 1u << s;
     };
     const bool lane0 = (tid & 31) == 0;
-    TmItem it;
-    for (long k = 0; seq_item(pl, k, &it); k++) {
+    const long nitems = (long)pl.ntiles * pl.nseg;
+    for (long item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const TmItem it = decode_item(pl, item);
         Coord x;
         x.x = it.x0 + sx; x.y = it.y0 + sy; x.z = it.z0 + sz; x.t = it.tb;
         const unsigned s3 = (unsigned)s3_of(g, x);
@@ -651,7 +641,6 @@ TmPlan make_plan(const Geom& g, int t_begin, int t_count, int nsm) {
     int bz = (int)(per_x / by + 0.5);
     bz = bz < 1 ? 1 : (bz > pl.ntz ? pl.ntz : bz);
     pl.by = by; pl.bz = bz;
-    pl.stagger = 0;
     return pl;
 }
 
@@ -789,13 +778,6 @@ bool launch_tmarch_fused(cudaStream_t st, const Geom& g, int t_begin, int t_coun
     if (ws && grid == (unsigned)nsm && nitems >= 2L * nsm && rsync && (pl.seg_len >= 32 || rsync == 2)) {
         ar.round_ctr = round_counter_for(dev, st);
         if (ar.round_ctr && cudaMemsetAsync(ar.round_ctr, 0, sizeof(unsigned long long), st) != cudaSuccess) { cudaGetLastError(); ar.round_ctr = nullptr; }
-    }
-    // staggered start: peer-store slabs marched in one segment by a persistent grid without the round barrier
-    // (GFB200_TMARCH_STAGGER=0: off, 2: also without peers -- test hook)
-    {
-        const int stg = env_int("GFB200_TMARCH_STAGGER", 1);
-        const bool peers = ar.peer_prev != nullptr || ar.peer_next != nullptr;
-        if (ws && stg && (peers || stg == 2) && ar.round_ctr == nullptr && grid == (unsigned)nsm && pl.nseg == 1 && t_count >= 2) pl.stagger = t_count;
     }
     if (env_int("GFB200_PEER_NOSTORE", 0)) ar.peer_prev = ar.peer_next = nullptr;  // timing experiments only: halos stay stale
 #define GFB_LAUNCH_TM(R, W, E)                                                                                                 \

@@ -112,34 +112,3 @@ def test_tmarch_reversibility_full_size_property(backend):
     assert np.abs(U.to_host() - U0).max() < 2e-12
     assert abs(r1.delta_hamiltonian + r2.delta_hamiltonian) < 1e-7 * abs(r1.initial_hamiltonian)
 
-
-def test_tmarch_staggered_start_matches_plain_march(backend, oracle):
-    """Staggered start of the persistent grid (TmPlan::stagger: CTA b marches slices [s_b, T) of its first tile first and that
-    tile's slices [0, s_b) last; used on peer-store t-slabs).  Forced on one GPU with GFB200_TMARCH_STAGGER=2 at a lattice with
-    more tiles than SMs (persistent grid), fused kick+drift against the plain march: identical arithmetic per link, so the fields
-    agree bitwise; the force is also checked against the oracle on a sample of time-slices."""
-    import gfb200
-
-    dims = (32, 32, 16, 8)  # 256 tiles > 148 SMs, one segment of 8 slices
-    U = gfb200.gauge_configuration(dims, backend=backend, start="hot", seed=91)
-    P = gfb200.gaussian_momenta(U, seed=4, sweep=0)
-    Uh, Ph = U.to_host().copy(), P.to_host().copy()
-    loops = gfb200.make_loops_fromname("plaquette")
-    action = gfb200.GaugeAction(U).push(3.0, loops + loops.adjoint())
-    md = gfb200.md_driver(U, action, steps=3, trajectory_length=0.15, integrator=gfb200.QPQ, fused=True)
-    gfb200.md_trajectory_(U, P, md)
-    u_plain, p_plain = U.to_host().copy(), P.to_host().copy()
-    U.upload(Uh)
-    P.upload(Ph)
-    os.environ["GFB200_TMARCH_STAGGER"] = "2"
-    try:
-        gfb200.md_trajectory_(U, P, md)
-        F = gfb200.gauge_momenta(U)
-        U2 = gfb200.gauge_configuration(dims, backend=backend).upload(Uh)
-        gfb200.md_force_(F, action, U2)
-    finally:
-        os.environ.pop("GFB200_TMARCH_STAGGER", None)
-    assert np.array_equal(U.to_host(), u_plain)
-    assert np.array_equal(P.to_host(), p_plain)
-    want = oracle.force(Uh, dims, 6.0)
-    assert np.abs(F.to_host() - want).max() < 1e-12 * np.abs(want).max()
