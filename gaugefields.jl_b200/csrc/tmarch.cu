@@ -470,6 +470,12 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long
     return v;
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 __device__ __noinline__ void tm_producer(const TmMaps& maps, const Geom& g, const TmPlan& pl, unsigned char* smem, uint64_t* bars,
                                          unsigned long long* round_ctr) {
     unsigned char* const sS = smem;
@@ -487,8 +493,14 @@ __device__ __noinline__ void tm_producer(const TmMaps& maps, const Geom& g, cons
         auto round_wait = [&]() {
             if (round_ctr != nullptr && round > 0) {
                 if (leader) {
+                    // The barrier is a locality hint, not a correctness condition, so it gives up after 2 ms: if the CTAs of this
+                    // launch are NOT all co-resident (another context's persistent kernel holds SMs) it must not deadlock.
                     const unsigned long long want = (unsigned long long)round * gridDim.x;
-                    while (ld_acquire_gpu(round_ctr) < want) __nanosleep(200);
+                    const unsigned long long t0 = global_timer_ns();
+                    while (ld_acquire_gpu(round_ctr) < want) {
+                        __nanosleep(200);
+                        if (global_timer_ns() - t0 > 2000000ull) break;
+                    }
                 }
                 __syncwarp();
             }
