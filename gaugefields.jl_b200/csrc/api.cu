@@ -1162,6 +1162,11 @@ static int fused_pass(gfb_gauge* g, const std::vector<double2*>& uin, const std:
                       const std::vector<double*>* zout, FusedArgs fa) {
     gfb_ctx* ctx = g->ctx;
     if (fa.c_rect != 0.0) {
+        {
+            bool su3 = true;
+            GFB_CHECK(links_are_unitary(g, &su3));
+            fa.full3 = !su3;
+        }
         // rectangle staples reach two sites away.  One slab: plain periodic addressing.  t-slabs: the one-slice halo slots are
         // not enough, so the pass runs on a wide copy of the slab (build_wide) and writes into the slab's own slices; the
         // output's one-slice halo is NOT exchanged here (callers clear halo_valid).

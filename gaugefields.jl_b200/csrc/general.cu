@@ -11,7 +11,8 @@
 // Here the sum over terms is ONE staple field V = c_plaq V_plaq + c_rect V_rect evaluated inside the fused
 // force -> (momentum / flow field) -> exp kernel, like the Wilson path (kernels.cu): one launch per kick or RK3 stage instead of
 // ~40 whole-field kernels per rectangle staple.  Links are read with plain coalesced 128-bit loads (the t-marching tile kernel
-// covers the plaquette stencil only); all products are full 3x3 (no unitarity assumption).  Rectangles reach two sites away, so
+// covers the plaquette stencil only); on SU(3) configurations (the handle's unitarity flag) the path products are two-row, otherwise
+// full 3x3 as in the reference.  Rectangles reach two sites away, so
 // on a t-slab decomposition the API first assembles a "wide" copy of the slab with two halo slices on either side in natural
 // t order (api.cu, build_wide): the kernels then read links at wide slice t and write their results at slab slice t - t_shift.
 #include "gfb_internal.h"
@@ -45,11 +46,46 @@ __device__ __forceinline__ M3 path_first(const double2* __restrict__ u, const Ge
     return m3_dagger(load_link(u, g, y, dir));
 }
 
+// the same for SU(3) links: rows 0,1 of the path product (72 instead of 108 FP64 instructions per factor); the third row is
+// rebuilt when the finished path is accumulated (acc_su3), as in the Wilson kernels (su3.cuh)
+__device__ __forceinline__ void path_step(R2& r, const double2* __restrict__ u, const Geom& g, Coord& y, int dir, int sgn) {
+    if (sgn > 0) {
+        const M3 l = load_link(u, g, y, dir);
+        r = r2_mul_nn(r, l);
+        y = step(g, y, dir, +1);
+    } else {
+        y = step(g, y, dir, -1);
+        const M3 l = load_link(u, g, y, dir);
+        r = r2_mul_nd(r, l);
+    }
+}
+__device__ __forceinline__ R2 path_first_r2(const double2* __restrict__ u, const Geom& g, Coord& y, int dir, int sgn) {
+    if (sgn > 0) {
+        const R2 r = r2_load_rows01(u + link_offset(g, y, dir), (unsigned)g.v3);
+        y = step(g, y, dir, +1);
+        return r;
+    }
+    y = step(g, y, dir, -1);
+    return r2_load_dag_rows01(u + link_offset(g, y, dir), (unsigned)g.v3);
+}
+template <bool FULL3>
+struct PathOf { typedef M3 type; };
+template <>
+struct PathOf<false> { typedef R2 type; };
+template <bool FULL3>
+__device__ __forceinline__ typename PathOf<FULL3>::type path_begin(const double2* __restrict__ u, const Geom& g, Coord& y, int dir, int sgn) {
+    if constexpr (FULL3) return path_first(u, g, y, dir, sgn);
+    else return path_first_r2(u, g, y, dir, sgn);
+}
+__device__ __forceinline__ void path_end(M3& v, const M3& m) { m3_add(v, m); }
+__device__ __forceinline__ void path_end(M3& v, const R2& r) { acc_su3(v, r); }
+
 // Sum of the 18 rectangle staples of link (x, mu): every path S from x to x+mu such that U_mu(x) S^dagger is a 1x2 or 2x1
 // rectangle (both orientations of the plane): for each nu != mu and s = +-1
 //   (a) s nu, mu, mu, -s nu, -mu      (2x1, the long side ahead of the link)
 //   (b) -mu, s nu, mu, mu, -s nu      (2x1, the long side behind the link)
 //   (c) s nu, s nu, mu, -s nu, -s nu  (1x2)
+template <bool FULL3>
 __device__ __forceinline__ M3 rect_staple_sum(const double2* __restrict__ u, const Geom& g, const Coord& x, int mu) {
     M3 v = m3_zero();
 #pragma unroll 1
@@ -60,30 +96,30 @@ __device__ __forceinline__ M3 rect_staple_sum(const double2* __restrict__ u, con
         for (int s = -1; s <= 1; s += 2) {
             {
                 Coord y = x;
-                M3 m = path_first(u, g, y, nu, s);
+                auto m = path_begin<FULL3>(u, g, y, nu, s);
                 path_step(m, u, g, y, mu, +1);
                 path_step(m, u, g, y, mu, +1);
                 path_step(m, u, g, y, nu, -s);
                 path_step(m, u, g, y, mu, -1);
-                m3_add(v, m);
+                path_end(v, m);
             }
             {
                 Coord y = x;
-                M3 m = path_first(u, g, y, mu, -1);
+                auto m = path_begin<FULL3>(u, g, y, mu, -1);
                 path_step(m, u, g, y, nu, s);
                 path_step(m, u, g, y, mu, +1);
                 path_step(m, u, g, y, mu, +1);
                 path_step(m, u, g, y, nu, -s);
-                m3_add(v, m);
+                path_end(v, m);
             }
             {
                 Coord y = x;
-                M3 m = path_first(u, g, y, nu, s);
+                auto m = path_begin<FULL3>(u, g, y, nu, s);
                 path_step(m, u, g, y, nu, s);
                 path_step(m, u, g, y, mu, +1);
                 path_step(m, u, g, y, nu, -s);
                 path_step(m, u, g, y, nu, -s);
-                m3_add(v, m);
+                path_end(v, m);
             }
         }
     }
@@ -99,8 +135,11 @@ __device__ __forceinline__ void m3_axpy(M3& acc, double a, const M3& m) {
 }
 
 // Z' = a * TAcoeffs(U_mu (c_plaq V_plaq + c_rect V_rect)^dag) + b * Z ;  Uout_mu = exp(c Z') Uin_mu
-template <bool READ_Z, bool WRITE_Z, bool DO_EXP>
-__global__ void __launch_bounds__(128, 3)
+#ifndef GFB_GEN_MINB
+#define GFB_GEN_MINB 3
+#endif
+template <bool READ_Z, bool WRITE_Z, bool DO_EXP, bool FULL3>
+__global__ void __launch_bounds__(128, GFB_GEN_MINB)
 k_force_general(Geom g, int t_begin, int t_count, int t_shift, const double2* __restrict__ uin, double2* __restrict__ uout, const double* __restrict__ zin,
                 double* __restrict__ zout, double a, double b, double c, double c_plaq, double c_rect) {
     const int mu = threadIdx.y;
@@ -110,8 +149,8 @@ k_force_general(Geom g, int t_begin, int t_count, int t_shift, const double2* __
     Coord xo = x;  // where the results go: the slab's own slice numbering
     xo.t -= t_shift;
     M3 v = m3_zero();
-    if (c_plaq != 0.0) m3_axpy(v, c_plaq, staple_sum<true>(uin, g, x, mu));
-    if (c_rect != 0.0) m3_axpy(v, c_rect, rect_staple_sum(uin, g, x, mu));
+    if (c_plaq != 0.0) m3_axpy(v, c_plaq, staple_sum<FULL3>(uin, g, x, mu));
+    if (c_rect != 0.0) m3_axpy(v, c_rect, rect_staple_sum<FULL3>(uin, g, x, mu));
     const M3 umu = load_link(uin, g, x, mu);
     double z[8];
     ta_coeffs_nd(umu, v, z);
@@ -124,7 +163,7 @@ k_force_general(Geom g, int t_begin, int t_count, int t_shift, const double2* __
         z[k] = w;
         if (WRITE_Z) zout[zo + k * zs] = w;
     }
-    if (DO_EXP) store_link(uout, g, xo, mu, mul_nn(exp_ta(z, c), umu));
+    if (DO_EXP) store_link(uout, g, xo, mu, FULL3 ? mul_nn(exp_ta(z, c), umu) : exp_ta_times_su3(z, c, umu));
 }
 
 // per site: sum_{mu<nu} Re tr P_munu  and  sum over the 12 rectangle loops of Re tr  (evaluate_GaugeAction's two building blocks)
@@ -258,7 +297,11 @@ void launch_force_general(cudaStream_t st, const Geom& g, int t_begin, int t_cou
     const long nsites = (long)g.v3 * t_count;
     if (nsites <= 0) return;
     dim3 block(32, 4), grid((unsigned)((nsites + 31) / 32));
-#define GFB_LAUNCH_FG(R, W, E) k_force_general<R, W, E><<<grid, block, 0, st>>>(g, t_begin, t_count, t_shift, uin, uout, zin, zout, fa.a, fa.b, fa.c, fa.c_plaq, fa.c_rect)
+#define GFB_LAUNCH_FG(R, W, E)                                                                                                                      \
+    do {                                                                                                                                             \
+        if (fa.full3) k_force_general<R, W, E, true><<<grid, block, 0, st>>>(g, t_begin, t_count, t_shift, uin, uout, zin, zout, fa.a, fa.b, fa.c, fa.c_plaq, fa.c_rect); \
+        else k_force_general<R, W, E, false><<<grid, block, 0, st>>>(g, t_begin, t_count, t_shift, uin, uout, zin, zout, fa.a, fa.b, fa.c, fa.c_plaq, fa.c_rect);       \
+    } while (0)
     if (fa.read_z) {
         if (fa.do_exp) GFB_LAUNCH_FG(true, true, true);
         else GFB_LAUNCH_FG(true, true, false);
