@@ -112,3 +112,30 @@ def test_tmarch_reversibility_full_size_property(backend):
     assert np.abs(U.to_host() - U0).max() < 2e-12
     assert abs(r1.delta_hamiltonian + r2.delta_hamiltonian) < 1e-7 * abs(r1.initial_hamiltonian)
 
+
+def test_tmarch_round_barrier_does_not_change_results(backend):
+    """The grid-wide round barrier of the persistent grid (TmArgs::round_ctr) only aligns the CTAs in time: a fused trajectory with
+    the barrier forced on (GFB200_TMARCH_ROUNDSYNC=2; by default it is on for marches of >= 32 slices, i.e. the 64^4 benchmark) must
+    be bitwise identical to the one without it.  32x32x32x8: 512 tiles = 3.5 rounds of the 148 CTAs."""
+    import gfb200
+
+    dims = (32, 32, 32, 8)
+    U = gfb200.gauge_configuration(dims, backend=backend, start="hot", seed=92)
+    P = gfb200.gaussian_momenta(U, seed=5, sweep=0)
+    U0, P0 = gfb200.copy_configuration(U), P.to_host().copy()
+    loops = gfb200.make_loops_fromname("plaquette")
+    action = gfb200.GaugeAction(U).push(3.0, loops + loops.adjoint())
+    md = gfb200.md_driver(U, action, steps=4, trajectory_length=0.2, integrator=gfb200.QPQ, fused=True)
+    out = []
+    for mode in ("0", "2"):
+        gfb200.copy_configuration_(U, U0)
+        P.upload(P0)
+        os.environ["GFB200_TMARCH_ROUNDSYNC"] = mode
+        try:
+            r = gfb200.md_trajectory_(U, P, md)
+        finally:
+            os.environ.pop("GFB200_TMARCH_ROUNDSYNC", None)
+        out.append((U.to_host().copy(), P.to_host().copy(), r.delta_hamiltonian))
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.array_equal(out[0][1], out[1][1])
+    assert out[0][2] == out[1][2]
