@@ -83,7 +83,23 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 #endif
 }
+#ifndef GFB_TM_WAIT_HINT
+#define GFB_TM_WAIT_HINT 1  // 1: try_wait with a suspend-time hint (the hardware parks the warp instead of re-issuing the probe)
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+#if GFB_TM_WAIT_HINT
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(20000u)
+        : "memory");
+#else
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -95,6 +111,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
         "}\n" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
+#endif
 }
 // global -> shared 4-D tensor copy (TMA), completion counted in bytes on `bar`
 __device__ __forceinline__ void tma_load_4d(unsigned dst_smem, const CUtensorMap* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
@@ -466,7 +483,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarr
 
 __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
     unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    // relaxed, not acquire: the counter orders nothing (a locality hint), and an acquire load at gpu scope invalidates the SM's L1
+    // on every poll (CCTL.IVALL), which is where the link warps' spilled descriptors live
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 
