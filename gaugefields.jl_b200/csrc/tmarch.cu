@@ -34,7 +34,7 @@
 #define GFB_TM_PIPE 0  // 1: operands requested one product ahead in program order (tm_step)
 #endif
 #ifndef GFB_TM_PREGS
-#define GFB_TM_PREGS 24  // registers per producer-group thread; the consumers get (64512 - 128*PREGS)/256 rounded down to 8
+#define GFB_TM_PREGS 40  // registers per producer-group thread; the consumers get (64512 - 128*PREGS)/256 rounded down to 8
 #endif
 #ifndef GFB_TM_RSYNC_LATE
 #define GFB_TM_RSYNC_LATE 1  // round barrier after (1) or before (0) the prologue copies of the next item
@@ -495,8 +495,13 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     return t;
 }
 
+#ifndef GFB_TM_NPW
+#define GFB_TM_NPW 4  // producer warps that issue tensor copies (of the 4 in the producer warpgroup); boxes are dealt round-robin
+#endif
 __device__ __noinline__ void tm_producer(const TmMaps& maps, const Geom& g, const TmPlan& pl, unsigned char* smem, uint64_t* bars,
-                                         unsigned long long* round_ctr) {
+                                         unsigned long long* round_ctr_arg, const int pw) {
+    // producer warp 0 owns the barrier bookkeeping (the byte count of a fill, the round counter); the others only add copies
+    unsigned long long* const round_ctr = pw == 0 ? round_ctr_arg : nullptr;
     unsigned char* const sS = smem;
     unsigned char* const sR = smem + tm::S_RING * tm::S_SLOT;
     unsigned ephase = ~0u;  // EMPTY barriers start "released": the first wait on each passes (parity of the preceding phase)
@@ -535,9 +540,11 @@ __device__ __noinline__ void tm_producer(const TmMaps& maps, const Geom& g, cons
             if (leader) {
                 uint64_t* const bar = bars + s;
                 unsigned char* const part = is_r ? sR + ring * tm::R_SLOT : sS + ring * tm::S_SLOT;
-                mbar_arrive_expect_tx(bar, (unsigned)((is_r ? tm::R_MATS : tm::S_MATS) * tm::MAT_BYTES));
+                // one arrival + the byte count of ALL boxes of the part; copies of the other producer warps may complete before
+                // this is performed (the transaction count goes negative, the phase cannot complete without the arrival)
+                if (pw == 0) mbar_arrive_expect_tx(bar, (unsigned)((is_r ? tm::R_MATS : tm::S_MATS) * tm::MAT_BYTES));
                 const int b0 = is_r ? tm::NBOX_S : 0, b1 = is_r ? tm::NBOX : tm::NBOX_S;
-                for (int b = b0; b < b1; b++) {
+                for (int b = b0 + pw; b < b1; b += GFB_TM_NPW) {
                     const int bcx = 2 * wrap(it.x0 + c_tm_box[b][0], g.nx), bcy = wrap(it.y0 + c_tm_box[b][1], g.ny), bcz = wrap(it.z0 + c_tm_box[b][2], g.nz);
                     tma_load_4d(smem_u32(part + c_tm_box[b][5]), &maps.m[c_tm_box[b][6]], bcx, bcy, bcz, tslot * 36 + c_tm_box[b][3] * 9, bar);
                 }
@@ -636,7 +643,7 @@ k_tmarch_ws(const __grid_constant__ TmMaps maps, const tm::Tables* __restrict__ 
     __syncthreads();
     if (threadIdx.x >= tm::NTHREADS) {
         reg_dec<GFB_TM_PREGS>();
-        if (threadIdx.x < tm::NTHREADS + 32) tm_producer(maps, g, pl, smem, bars, ar.round_ctr);
+        if (threadIdx.x < tm::NTHREADS + 32 * GFB_TM_NPW) tm_producer(maps, g, pl, smem, bars, ar.round_ctr, (threadIdx.x - tm::NTHREADS) >> 5);
         return;
     }
     reg_inc<((64512 - 128 * GFB_TM_PREGS) / 256) & ~7>();
