@@ -464,9 +464,9 @@ k_tmarch_fused(const __grid_constant__ TmMaps maps, const tm::Tables* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Variant B (default): warp-specialised.  Warps 0-7 are the 256 link-threads (consumers), warps 8-11 a producer warpgroup of
-// which one warp issues every tensor copy.  Registers move from the producer group to the consumers (setmaxnreg: 24 / 240 per
-// thread: 128*24 + 256*240 = the 64512 registers of a 384 x 168 launch).  No CTA-wide barrier in the march: every ring slot
+// Variant B (default): warp-specialised.  Warps 0-7 are the 256 link-threads (consumers), warps 8-11 a producer warpgroup whose
+// GFB_TM_NPW warps issue the tensor copies (boxes dealt round-robin).  Registers move from the producer group to the consumers
+// (setmaxnreg: 40 / 232 per thread, of the 64512 registers of a 384 x 168 launch).  No CTA-wide barrier in the march: every ring slot
 // has a FULL mbarrier (the copies' byte count) and an EMPTY mbarrier (one arrival per consumer warp, given as soon as the
 // warp has consumed the slot's operands, i.e. BEFORE its exponential), so the eight consumer warps drift apart by up to a
 // slice instead of meeting once per step behind the warp that also had to issue 21 copies (variant A: 8 % barrier stall,
